@@ -1,0 +1,195 @@
+/* rtree_b200.h -- the C ABI of the B200 batched query engine (librtree_b200.so).
+ *
+ * This is the drop-in boundary for the read-only query path of ehwan/R-Star-Tree.
+ * The reference has no FFI layer -- its "GPU support" is RTree::flatten()
+ * (reference include/RTree/rtree.hpp:966-981) returning host vectors the user is told
+ * to upload themselves (reference README.md:265-274).  These entry points are what a
+ * binding for that path attaches to:
+ *
+ *   rt_upload        <- consumes what RTree::flatten_device() emits, i.e. the
+ *                       flatten_result_t of reference rtree.hpp:852-870 re-laid out
+ *   rt_query_boxes   <- replaces a host loop of RTree::search(filter, functor)
+ *                       (reference rtree.hpp:1141-1146, hot loop :984-1019) with the
+ *                       canonical closed-overlap filter (reference
+ *                       example/sample/sample.cpp:48-54, test/rtree.cpp:403) and the
+ *                       leaf test geometry_traits<aabb>::is_inside (reference
+ *                       include/RTree/aabb.hpp:206-210; test/rtree.cpp:390)
+ *   rt_query_rays    <- the same search() driven by a stateful slab-test filter
+ *                       (legal per reference rtree.hpp:1145); all-hits, closest-hit,
+ *                       any-hit (functor returning true, reference rtree.hpp:994-997)
+ *   rt_free          <- releases the device copy
+ *
+ * Plain C, plain pointers and sizes; no exceptions cross the boundary.  Every call
+ * returns RT_OK (0) or a negative RT_E_* code; rt_last_error() gives the text.
+ * There is NO CPU fallback: without a CUDA device every call fails with RT_E_CUDA.
+ *
+ * Threading: calls on one handle are serialised by the caller; different handles
+ * (different GPUs) may be driven from different host threads.
+ */
+#ifndef RTREE_B200_H
+#define RTREE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1u
+
+/* error codes */
+#define RT_OK 0
+#define RT_E_INVALID (-1)     /* bad argument / descriptor */
+#define RT_E_UNSUPPORTED (-2) /* (scalar, dim, width, key kind, mode) not instantiated */
+#define RT_E_CUDA (-3)        /* CUDA runtime error, or no device */
+#define RT_E_NOMEM (-4)       /* host or device allocation failed */
+#define RT_E_INTERNAL (-5)
+
+/* rt_tree_desc.scalar */
+#define RT_F32 0u
+#define RT_F64 1u
+#define RT_I32 2u
+
+/* rt_tree_desc.key_kind */
+#define RT_KEY_POINT 0u /* leaf blocks store one corner: p[dim][W], id[W]            */
+#define RT_KEY_BOX 1u   /* leaf blocks look like internal ones: lo, hi, id           */
+
+/* memory spaces */
+#define RT_MEM_HOST 0u
+#define RT_MEM_DEVICE 1u
+
+/* rt_query_boxes mode = the leaf predicate (the node filter is always the closed
+ * overlap  !(hi < qmin || lo > qmax)  per axis)                                     */
+#define RT_POINT_IN_BOX 0u /* point keys:  !(p < qmin || p > qmax) per axis           */
+#define RT_INTERSECTS 1u   /* box keys:    closed overlap with the key box            */
+#define RT_CONTAINS 2u     /* box keys:    !(klo < qmin || khi > qmax) per axis       */
+
+/* rt_query_rays mode */
+#define RT_RAY_ALL_HITS 0u /* CSR of key ids whose AABB the ray hits                  */
+#define RT_RAY_CLOSEST 1u  /* (t, id): least entry distance, ties to the smaller id   */
+#define RT_RAY_ANY 2u      /* one byte per ray                                        */
+
+/* flags (OR-ed) */
+#define RT_QUERIES_ON_DEVICE 0x1u /* the query pointer is device memory on the tree's GPU */
+#define RT_RESULT_ON_DEVICE 0x2u  /* leave the result in device memory (no D2H copy)      */
+#define RT_UNSORTED 0x4u          /* per-query ids in traversal order (still deterministic)*/
+#define RT_COUNT_ONLY 0x8u        /* fill offsets / total only, no ids                    */
+#define RT_COLLECT_VISITS 0x10u   /* also count node visits (rt_stats), slower            */
+#define RT_NO_REORDER 0x20u       /* process queries in input order (no coherence pass)   */
+
+/* An id slot that holds no entry.  Ids / value counts must stay below it.            */
+#define RT_INVALID_ID 0xFFFFFFFFu
+
+typedef struct rt_tree rt_tree; /* opaque; owns device memory on ONE GPU */
+
+/* What RTree::flatten_device() fills (r-star-tree_b200/include/RTree/device_layout.hpp).
+ *
+ * Nodes are renumbered in breadth-first (level) order: node 0 is the root, level l
+ * occupies [level_node_begin[l], level_node_begin[l+1]), leaves are the last level.
+ * `blocks` holds one fixed-width block per node, W = width slots each:
+ *
+ *   internal node i :  blocks + i * internal_stride
+ *        lo[dim][W] | hi[dim][W] | child[W]      child = node index, RT_INVALID_ID if empty
+ *   leaf node j (j counted from the first leaf) :  blocks + leaf_offset + j * leaf_stride
+ *        RT_KEY_POINT :  p[dim][W] | id[W]
+ *        RT_KEY_BOX   :  lo[dim][W] | hi[dim][W] | id[W]
+ *
+ * Rows are W consecutive scalars (structure of arrays), every block is 16-byte
+ * aligned, empty slots carry an inverted box and RT_INVALID_ID.                      */
+typedef struct rt_tree_desc
+{
+  uint32_t abi_version; /* RT_ABI_VERSION */
+  uint32_t dim;         /* 1..8 */
+  uint32_t scalar;      /* RT_F32 | RT_F64 | RT_I32 */
+  uint32_t width;       /* W: MAX_ENTRIES rounded up to 8 or 16 */
+  uint32_t max_entries; /* Config::MAX_ENTRIES of the tree that was flattened */
+  uint32_t key_kind;    /* RT_KEY_POINT | RT_KEY_BOX */
+  uint32_t leaf_level;  /* flatten_result_t::leaf_level */
+  uint32_t num_levels;  /* leaf_level + 1 */
+  uint32_t num_nodes;
+  uint32_t num_values;  /* number of leaf entries */
+  uint32_t internal_stride; /* bytes between internal blocks */
+  uint32_t leaf_stride;     /* bytes between leaf blocks */
+  uint64_t leaf_offset;     /* byte offset of the first leaf block */
+  uint64_t blocks_bytes;
+  const void* blocks;
+  const uint32_t* level_node_begin; /* [num_levels + 1], host memory */
+  uint32_t blocks_memory;           /* RT_MEM_HOST | RT_MEM_DEVICE (same GPU) */
+  uint32_t reserved;
+} rt_tree_desc;
+
+/* CSR hit lists.  The buffers belong to the tree handle and stay valid until the next
+ * query on that handle or rt_free().  ids[offsets[q] .. offsets[q+1]) are the hits of
+ * query q, ascending unless RT_UNSORTED.                                             */
+typedef struct rt_hits
+{
+  uint64_t n_queries;
+  uint64_t total;
+  const uint64_t* offsets; /* [n_queries + 1] */
+  const uint32_t* ids;     /* [total]; NULL with RT_COUNT_ONLY */
+  uint32_t memory;         /* RT_MEM_HOST (pinned) | RT_MEM_DEVICE */
+  uint32_t reserved;
+} rt_hits;
+
+typedef struct rt_ray_result
+{
+  uint64_t n_rays;
+  uint64_t n_hit;   /* rays with at least one hit (closest / any), total hits (all) */
+  rt_hits hits;     /* RT_RAY_ALL_HITS */
+  const float* t;   /* RT_RAY_CLOSEST: entry distance, +inf on a miss */
+  const uint32_t* id; /* RT_RAY_CLOSEST: key id, RT_INVALID_ID on a miss */
+  const uint8_t* any; /* RT_RAY_ANY */
+  uint32_t memory;
+  uint32_t reserved;
+} rt_ray_result;
+
+/* Timings of the LAST query call on the handle (CUDA events on the handle's stream)
+ * and, with RT_COLLECT_VISITS, the node-visit totals that define the algorithmic
+ * bytes of the batch.                                                                 */
+typedef struct rt_stats
+{
+  float total_ms;    /* first H2D to last D2H */
+  float h2d_ms;
+  float reorder_ms;  /* coherence pass over the queries */
+  float traverse_ms; /* the traversal kernel(s) */
+  float finish_ms;   /* scan + compaction + deferred queries */
+  float d2h_ms;
+  uint32_t kernel_launches; /* kernels of this library launched by the call */
+  uint32_t deferred_queries; /* queries answered by the second traversal */
+  uint64_t visits_internal;
+  uint64_t visits_leaf;
+  uint64_t algorithmic_bytes; /* SURVEY.md 8d formula on the visit totals */
+} rt_stats;
+
+/* Copy the tree image to `device` (cudaSetDevice(device) is called by every entry
+ * point).  *out receives the handle.                                                  */
+int rt_upload(const rt_tree_desc* desc, int device, rt_tree** out);
+
+/* boxes: [n][2][dim] scalars of the tree's type, min corner then max corner.          */
+int rt_query_boxes(rt_tree* tree, const void* boxes, uint64_t n, uint32_t mode,
+                   uint32_t flags, rt_hits* out);
+
+/* rays: [n][7] floats = origin[3], 1/direction[3] (computed by the caller so that
+ * every consumer sees the same bits), tmax; tmin is 0.  3-D f32 trees only.            */
+int rt_query_rays(rt_tree* tree, const float* rays, uint64_t n, uint32_t mode,
+                  uint32_t flags, rt_ray_result* out);
+
+/* Release the handle and every buffer it handed out.  NULL is a no-op.                */
+void rt_free(rt_tree* tree);
+
+/* ---- auxiliaries -------------------------------------------------------------- */
+/* Launch on this CUDA stream (a cudaStream_t) instead of the handle's own.          */
+int rt_set_stream(rt_tree* tree, void* cuda_stream);
+int rt_get_stats(const rt_tree* tree, rt_stats* out);
+/* Device copy of the blocks, e.g. to broadcast the tree to peer GPUs.               */
+int rt_tree_device_blocks(const rt_tree* tree, void** device_ptr, uint64_t* bytes);
+int rt_tree_get_desc(const rt_tree* tree, rt_tree_desc* out);
+const char* rt_last_error(void);
+uint32_t rt_abi_version(void);
+/* Number of CUDA devices visible, or RT_E_CUDA.                                      */
+int rt_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTREE_B200_H */

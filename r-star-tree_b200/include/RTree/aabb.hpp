@@ -1,0 +1,3 @@
+// RTree/aabb.hpp -- kept so that reference-style includes keep working.
+#pragma once
+#include "geometry.hpp"

@@ -1,0 +1,304 @@
+// RTree/device_layout.hpp -- host side (header-only C++17) of rtree-b200.
+//
+// flatten_device(): the step the reference leaves to the user
+// (reference README.md:265-274, "upload the buffers yourself").  It takes a
+// flatten_result_t -- ours or the reference's, the function is duck-typed on the
+// field names of reference include/RTree/rtree.hpp:841-870 -- and re-lays it out for
+// the GPU kernels:
+//
+//   * nodes renumbered breadth-first, so a level is one contiguous range, siblings
+//     are adjacent and the top of the tree is a small prefix of the buffer;
+//   * one fixed-width block per node, W = MAX_ENTRIES rounded up to 8 or 16 slots,
+//     structure-of-arrays by axis:  lo[dim][W] | hi[dim][W] | child[W]; a warp lane
+//     reads "its" child with one coalesced load per row;
+//   * leaves of point-keyed trees keep one corner only:  p[dim][W] | id[W];
+//   * empty slots hold an inverted box and RT_INVALID_ID, so lanes need no size test.
+//
+// The result is a POD descriptor (rt_tree_desc, include/rtree_b200.h) plus one
+// contiguous 256-byte aligned host buffer; hand desc() to rt_upload().
+#pragma once
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <stdexcept>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include <rtree_b200.h>
+
+#include "geometry.hpp"
+
+namespace eh
+{
+namespace rtree
+{
+
+/// what a leaf slot reports as the "id" of a hit
+enum class id_source
+{
+  data_index,  ///< index into flatten_result_t::data (always possible)
+  mapped_value ///< static_cast<uint32_t>(data[index]); integral mapped types only
+};
+
+namespace detail
+{
+template <typename Geometry, typename Key>
+struct key_is_box : std::is_same<Geometry, Key>
+{
+};
+
+template <typename S>
+struct scalar_code;
+template <>
+struct scalar_code<float>
+{
+  constexpr static std::uint32_t value = RT_F32;
+};
+template <>
+struct scalar_code<double>
+{
+  constexpr static std::uint32_t value = RT_F64;
+};
+template <>
+struct scalar_code<std::int32_t>
+{
+  constexpr static std::uint32_t value = RT_I32;
+};
+
+/// 256-byte aligned, zero-initialised byte buffer
+class aligned_bytes
+{
+  unsigned char* _p = nullptr;
+  std::size_t _n = 0;
+
+public:
+  aligned_bytes() = default;
+  explicit aligned_bytes(std::size_t n)
+      : _n(n)
+  {
+    const std::size_t rounded = (n + 255) / 256 * 256;
+    _p = static_cast<unsigned char*>(std::aligned_alloc(256, rounded ? rounded : 256));
+    if (_p == nullptr)
+      throw std::bad_alloc();
+    std::memset(_p, 0, rounded ? rounded : 256);
+  }
+  aligned_bytes(aligned_bytes&& rhs) noexcept
+      : _p(rhs._p)
+      , _n(rhs._n)
+  {
+    rhs._p = nullptr;
+    rhs._n = 0;
+  }
+  aligned_bytes& operator=(aligned_bytes&& rhs) noexcept
+  {
+    if (this != &rhs)
+    {
+      std::free(_p);
+      _p = rhs._p;
+      _n = rhs._n;
+      rhs._p = nullptr;
+      rhs._n = 0;
+    }
+    return *this;
+  }
+  aligned_bytes(aligned_bytes const&) = delete;
+  aligned_bytes& operator=(aligned_bytes const&) = delete;
+  ~aligned_bytes() { std::free(_p); }
+  unsigned char* data() { return _p; }
+  unsigned char const* data() const { return _p; }
+  std::size_t size() const { return _n; }
+};
+
+template <typename Mapped>
+inline typename std::enable_if<std::is_integral<Mapped>::value && sizeof(Mapped) <= 4, std::uint32_t>::type
+mapped_as_id(Mapped const& v)
+{
+  return static_cast<std::uint32_t>(v);
+}
+template <typename Mapped>
+inline typename std::enable_if<!(std::is_integral<Mapped>::value && sizeof(Mapped) <= 4), std::uint32_t>::type
+mapped_as_id(Mapped const&)
+{
+  throw std::invalid_argument("id_source::mapped_value needs an integral mapped type of <= 32 bits");
+}
+} // namespace detail
+
+/// block width for a node capacity: 8 or 16 slots
+constexpr inline std::uint32_t device_block_width(std::uint32_t max_entries)
+{
+  return max_entries <= 8 ? 8u : 16u;
+}
+
+/// The tree image flatten_device() produces.  Movable, not copyable.
+struct device_tree_t
+{
+  std::uint32_t dim = 0;
+  std::uint32_t scalar = 0;
+  std::uint32_t width = 0;
+  std::uint32_t max_entries = 0;
+  std::uint32_t key_kind = 0;
+  std::uint32_t leaf_level = 0;
+  std::uint32_t num_values = 0;
+  std::uint32_t internal_stride = 0;
+  std::uint32_t leaf_stride = 0;
+  std::uint64_t leaf_offset = 0;
+  /// first node of every level, plus the total: [leaf_level + 2]
+  std::vector<std::uint32_t> level_node_begin;
+  /// new (breadth-first) index -> index in flatten_result_t::nodes
+  std::vector<std::uint32_t> bfs_to_dfs;
+  detail::aligned_bytes blocks;
+
+  std::uint32_t num_levels() const { return leaf_level + 1; }
+  std::uint32_t num_nodes() const { return level_node_begin.empty() ? 0 : level_node_begin.back(); }
+
+  /// descriptor for rt_upload(); borrows this object's buffers
+  rt_tree_desc desc() const
+  {
+    rt_tree_desc d;
+    std::memset(&d, 0, sizeof d);
+    d.abi_version = RT_ABI_VERSION;
+    d.dim = dim;
+    d.scalar = scalar;
+    d.width = width;
+    d.max_entries = max_entries;
+    d.key_kind = key_kind;
+    d.leaf_level = leaf_level;
+    d.num_levels = num_levels();
+    d.num_nodes = num_nodes();
+    d.num_values = num_values;
+    d.internal_stride = internal_stride;
+    d.leaf_stride = leaf_stride;
+    d.leaf_offset = leaf_offset;
+    d.blocks_bytes = blocks.size();
+    d.blocks = blocks.data();
+    d.level_node_begin = level_node_begin.data();
+    d.blocks_memory = RT_MEM_HOST;
+    return d;
+  }
+};
+
+/// Re-lay a flatten_result_t (field names of reference rtree.hpp:841-870) as device
+/// blocks.  MaxEntries / KeyIsBox describe the tree that was flattened.
+template <std::uint32_t MaxEntries, bool KeyIsBox, typename FlattenResult>
+device_tree_t flatten_device(FlattenResult const& flat, id_source ids = id_source::data_index)
+{
+  using geometry_type = typename std::decay<decltype(flat.children_bound[0])>::type;
+  using gtraits = geometry_traits<geometry_type>;
+  using scalar = typename gtraits::scalar_type;
+  constexpr std::uint32_t D = static_cast<std::uint32_t>(gtraits::DIM);
+  constexpr std::uint32_t W = device_block_width(MaxEntries);
+  static_assert(MaxEntries <= 16, "device blocks are at most 16 slots wide");
+  static_assert(D >= 1 && D <= 8, "device blocks support 1..8 dimensions");
+
+  if (flat.nodes.empty())
+    throw std::invalid_argument("flatten_device: empty flatten_result_t (no root node)");
+  if (flat.children.size() >= 0xFFFFFFFFull || flat.data.size() >= 0xFFFFFFFFull)
+    throw std::length_error("flatten_device: more than 2^32-2 entries");
+
+  device_tree_t out;
+  out.dim = D;
+  out.scalar = detail::scalar_code<scalar>::value;
+  out.width = W;
+  out.max_entries = MaxEntries;
+  out.key_kind = KeyIsBox ? RT_KEY_BOX : RT_KEY_POINT;
+  out.leaf_level = flat.leaf_level;
+  out.num_values = static_cast<std::uint32_t>(flat.data.size());
+  out.internal_stride = W * (2 * D * sizeof(scalar) + 4);
+  out.leaf_stride = KeyIsBox ? out.internal_stride : W * (D * sizeof(scalar) + 4);
+
+  // ---- breadth-first renumbering (levels are implicit in the flat form: a node is a
+  //      leaf iff it is leaf_level steps below node 0, reference test/rtree.cpp:383)
+  const std::uint32_t n_nodes = static_cast<std::uint32_t>(flat.nodes.size());
+  std::vector<std::uint32_t>& order = out.bfs_to_dfs;
+  order.reserve(n_nodes);
+  order.push_back(flat.root);
+  out.level_node_begin.push_back(0);
+  for (std::uint32_t level = 0; level < flat.leaf_level; ++level)
+  {
+    const std::uint32_t begin = out.level_node_begin[level];
+    const std::uint32_t end = static_cast<std::uint32_t>(order.size());
+    out.level_node_begin.push_back(end);
+    for (std::uint32_t b = begin; b < end; ++b)
+    {
+      auto const& node = flat.nodes[order[b]];
+      if (node.size > MaxEntries)
+        throw std::invalid_argument("flatten_device: node wider than MAX_ENTRIES");
+      for (std::uint32_t c = 0; c < node.size; ++c)
+        order.push_back(flat.children[node.offset + c]);
+    }
+  }
+  out.level_node_begin.push_back(static_cast<std::uint32_t>(order.size()));
+  if (order.size() != n_nodes)
+    throw std::invalid_argument("flatten_device: nodes unreachable from the root");
+
+  const std::uint32_t leaf_begin = out.level_node_begin[flat.leaf_level];
+  const std::uint32_t n_leaves = n_nodes - leaf_begin;
+  const std::uint64_t internal_bytes = std::uint64_t(leaf_begin) * out.internal_stride;
+  out.leaf_offset = (internal_bytes + 127) / 128 * 128;
+  out.blocks = detail::aligned_bytes(out.leaf_offset + std::uint64_t(n_leaves) * out.leaf_stride);
+
+  const scalar empty_lo = std::numeric_limits<scalar>::has_infinity
+                              ? std::numeric_limits<scalar>::infinity()
+                              : std::numeric_limits<scalar>::max();
+  const scalar empty_hi = std::numeric_limits<scalar>::has_infinity
+                              ? -std::numeric_limits<scalar>::infinity()
+                              : std::numeric_limits<scalar>::lowest();
+
+  // children of consecutive breadth-first nodes are consecutive breadth-first nodes
+  std::uint32_t next_child = 1;
+  unsigned char* base = out.blocks.data();
+  for (std::uint32_t b = 0; b < n_nodes; ++b)
+  {
+    auto const& node = flat.nodes[order[b]];
+    const bool is_leaf = b >= leaf_begin;
+    unsigned char* block = is_leaf ? base + out.leaf_offset + std::uint64_t(b - leaf_begin) * out.leaf_stride
+                                   : base + std::uint64_t(b) * out.internal_stride;
+    const bool one_corner = is_leaf && !KeyIsBox;
+    scalar* lo = reinterpret_cast<scalar*>(block);
+    scalar* hi = one_corner ? nullptr : lo + D * W;
+    std::uint32_t* link = reinterpret_cast<std::uint32_t*>(block + (one_corner ? D : 2 * D) * W * sizeof(scalar));
+    if (is_leaf && node.size > MaxEntries)
+      throw std::invalid_argument("flatten_device: leaf wider than MAX_ENTRIES");
+    for (std::uint32_t c = 0; c < W; ++c)
+    {
+      if (c < node.size)
+      {
+        geometry_type const& g = flat.children_bound[node.offset + c];
+        for (std::uint32_t d = 0; d < D; ++d)
+        {
+          lo[d * W + c] = gtraits::min_point(g, static_cast<int>(d));
+          if (hi != nullptr)
+            hi[d * W + c] = gtraits::max_point(g, static_cast<int>(d));
+        }
+        if (is_leaf)
+        {
+          const std::uint32_t data_index = flat.children[node.offset + c];
+          link[c] = (ids == id_source::mapped_value) ? detail::mapped_as_id(flat.data[data_index])
+                                                     : data_index;
+        }
+        else
+        {
+          link[c] = next_child++;
+        }
+      }
+      else
+      {
+        for (std::uint32_t d = 0; d < D; ++d)
+        {
+          lo[d * W + c] = empty_lo;
+          if (hi != nullptr)
+            hi[d * W + c] = empty_hi;
+        }
+        link[c] = RT_INVALID_ID;
+      }
+    }
+  }
+  return out;
+}
+
+} // namespace rtree
+} // namespace eh

@@ -1,0 +1,3 @@
+// RTree/iterator.hpp -- kept so that reference-style includes keep working.
+#pragma once
+#include "node.hpp"

@@ -1,0 +1,3 @@
+// RTree/quadratic_split.hpp -- kept so that reference-style includes keep working.
+#pragma once
+#include "split.hpp"
