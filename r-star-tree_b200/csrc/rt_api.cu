@@ -1,0 +1,833 @@
+// rt_api.cu -- the C ABI of include/rtree_b200.h: device buffers, streams, events and the
+// per-call pipeline around the traversal kernels.  No query-path arithmetic lives here.
+//
+// rt_query_boxes pipeline (default flags), all on the handle's stream:
+//   H2D queries -> reorder (Morton cells) -> traversal PASS_STASH (counts + sorted short
+//   lists into the stash) -> scan (CSR offsets) -> [8-byte D2H: total, #deferred] ->
+//   gather stash -> PASS_WRITE over the deferred queries only -> sort their long lists ->
+//   D2H offsets + ids.
+// With RT_COLLECT_VISITS / RT_COUNT_ONLY the plain two-pass form (PASS_COUNT[_STATS],
+// scan, PASS_WRITE over all queries) runs instead.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rt_common.cuh"
+
+namespace
+{
+thread_local std::string g_last_error = "";
+
+int fail(int code, const std::string& what)
+{
+  g_last_error = what;
+  return code;
+}
+
+#define RT_CUDA(expr)                                                                         \
+  do                                                                                          \
+  {                                                                                           \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+    {                                                                                         \
+      cudaGetLastError();                                                                     \
+      return fail(e_ == cudaErrorMemoryAllocation ? RT_E_NOMEM : RT_E_CUDA,                   \
+                  std::string(#expr) + ": " + cudaGetErrorString(e_));                        \
+    }                                                                                         \
+  } while (0)
+
+// grow-only device / pinned-host buffers owned by a handle
+struct DevBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes)
+  {
+    if (bytes <= cap)
+      return cudaSuccess;
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess)
+    {
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      if (e != cudaSuccess)
+        return e;
+      cap = bytes;
+      return cudaSuccess;
+    }
+    cap = want;
+    return cudaSuccess;
+  }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const
+  {
+    return static_cast<T*>(p);
+  }
+};
+struct HostBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes)
+  {
+    if (bytes <= cap)
+      return cudaSuccess;
+    if (p)
+      cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess)
+      return e;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release()
+  {
+    if (p)
+      cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const
+  {
+    return static_cast<T*>(p);
+  }
+};
+
+// device-side counters of one call (one 64-byte block, zeroed per call)
+struct Counters
+{
+  unsigned long long work;        // query chunk cursor
+  unsigned long long stash_cursor;
+  unsigned long long visits[3];   // internal visits, leaf visits, rays with a hit
+  unsigned long long total;       // filled by copying offsets[n]
+  uint32_t deferred;
+  uint32_t big;
+  uint32_t pad[2];
+};
+static_assert(sizeof(Counters) == 64, "Counters layout");
+
+enum
+{
+  EV_BEGIN = 0,
+  EV_H2D,
+  EV_REORDER,
+  EV_TRAVERSE,
+  EV_FINISH,
+  EV_D2H,
+  EV_COUNT
+};
+} // namespace
+
+struct rt_tree
+{
+  int device = 0;
+  rt_tree_desc desc;
+  std::vector<uint32_t> levels;
+  rtb::TreeDev dev;
+  unsigned char* d_blocks = nullptr;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[EV_COUNT] = {};
+  // extra events bracketing the second traversal
+  cudaEvent_t ev_t2_begin = nullptr, ev_t2_end = nullptr;
+
+  DevBuf d_queries, d_order, d_counts, d_offsets, d_ids, d_stash, d_stash_pos, d_deferred, d_big,
+      d_scratch, d_counters, d_ray_t, d_ray_id, d_ray_any;
+  HostBuf h_counters, h_offsets, h_ids, h_ray_t, h_ray_id, h_ray_any;
+  unsigned long long stash_wanted = 0; // pool size the last call would have needed
+  rt_stats stats;
+};
+
+namespace
+{
+int check_desc(const rt_tree_desc* d)
+{
+  if (d == nullptr)
+    return fail(RT_E_INVALID, "rt_upload: desc is NULL");
+  if (d->abi_version != RT_ABI_VERSION)
+    return fail(RT_E_INVALID, "rt_upload: abi_version mismatch");
+  if (d->dim < 1 || d->dim > 8)
+    return fail(RT_E_INVALID, "rt_upload: dim must be 1..8");
+  if (d->scalar > RT_I32)
+    return fail(RT_E_INVALID, "rt_upload: unknown scalar type");
+  if (d->width != 8 && d->width != 16)
+    return fail(RT_E_UNSUPPORTED, "rt_upload: block width must be 8 or 16");
+  if (d->key_kind > RT_KEY_BOX)
+    return fail(RT_E_INVALID, "rt_upload: unknown key kind");
+  if (d->num_levels != d->leaf_level + 1 || d->num_levels > 64)
+    return fail(RT_E_INVALID, "rt_upload: num_levels must be leaf_level + 1 (<= 64)");
+  if (d->level_node_begin == nullptr || d->blocks == nullptr)
+    return fail(RT_E_INVALID, "rt_upload: NULL buffer in desc");
+  if (d->num_nodes == 0 || d->level_node_begin[0] != 0 || d->level_node_begin[d->num_levels] != d->num_nodes)
+    return fail(RT_E_INVALID, "rt_upload: level_node_begin inconsistent with num_nodes");
+  for (uint32_t l = 0; l < d->num_levels; ++l)
+  {
+    if (d->level_node_begin[l] >= d->level_node_begin[l + 1])
+      return fail(RT_E_INVALID, "rt_upload: empty level in level_node_begin");
+  }
+  if (d->level_node_begin[1] != 1)
+    return fail(RT_E_INVALID, "rt_upload: level 0 must hold exactly the root");
+  const uint32_t s = d->scalar == RT_F64 ? 8u : 4u;
+  const uint32_t internal = d->width * (2 * d->dim * s + 4);
+  const uint32_t leaf = d->key_kind == RT_KEY_BOX ? internal : d->width * (d->dim * s + 4);
+  if (d->internal_stride < internal || d->leaf_stride < leaf || d->internal_stride % 16 || d->leaf_stride % 16
+      || d->leaf_offset % 16)
+    return fail(RT_E_INVALID, "rt_upload: block strides / offsets too small or not 16-byte aligned");
+  const uint32_t leaf_begin = d->level_node_begin[d->leaf_level];
+  const uint64_t need_internal = (uint64_t)leaf_begin * d->internal_stride;
+  const uint64_t need = d->leaf_offset + (uint64_t)(d->num_nodes - leaf_begin) * d->leaf_stride;
+  if (d->leaf_offset < need_internal || d->blocks_bytes < need)
+    return fail(RT_E_INVALID, "rt_upload: blocks_bytes smaller than the layout needs");
+  if (d->num_values >= RT_INVALID_ID)
+    return fail(RT_E_INVALID, "rt_upload: too many values");
+  return RT_OK;
+}
+
+int use_device(const rt_tree* t)
+{
+  RT_CUDA(cudaSetDevice(t->device));
+  return RT_OK;
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b)
+{
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return 0.f;
+  }
+  return ms;
+}
+
+uint64_t algorithmic_bytes_boxes(const rt_tree* t, uint64_t n, uint64_t total, uint64_t v_int, uint64_t v_leaf)
+{
+  // V_int*B_int + V_leaf*B_leaf + query bytes + 8 (CSR offset) + 4*hits
+  const uint64_t s = t->desc.scalar == RT_F64 ? 8 : 4;
+  const uint64_t M = t->desc.max_entries, D = t->desc.dim;
+  const uint64_t b_int = M * (2 * D * s + 4);
+  const uint64_t b_leaf = t->desc.key_kind == RT_KEY_BOX ? b_int : M * (D * s + 4);
+  return v_int * b_int + v_leaf * b_leaf + n * (2 * D * s + 8) + 4 * total;
+}
+} // namespace
+
+extern "C"
+{
+
+const char* rt_last_error(void) { return g_last_error.c_str(); }
+uint32_t rt_abi_version(void) { return RT_ABI_VERSION; }
+
+int rt_device_count(void)
+{
+  int n = 0;
+  RT_CUDA(cudaGetDeviceCount(&n));
+  return n;
+}
+
+int rt_upload(const rt_tree_desc* desc, int device, rt_tree** out)
+{
+  if (out == nullptr)
+    return fail(RT_E_INVALID, "rt_upload: out is NULL");
+  *out = nullptr;
+  int rc = check_desc(desc);
+  if (rc != RT_OK)
+    return rc;
+  if (rtb::find_box_kernel(desc->scalar, desc->dim, desc->width, desc->key_kind, RT_INTERSECTS) == nullptr)
+    return fail(RT_E_UNSUPPORTED, "rt_upload: no kernel instantiated for this (scalar, dim, width)");
+  int count = 0;
+  RT_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count)
+    return fail(RT_E_CUDA, "rt_upload: no such CUDA device");
+  RT_CUDA(cudaSetDevice(device));
+
+  rt_tree* t = new (std::nothrow) rt_tree();
+  if (t == nullptr)
+    return fail(RT_E_NOMEM, "rt_upload: out of host memory");
+  t->device = device;
+  t->desc = *desc;
+  t->levels.assign(desc->level_node_begin, desc->level_node_begin + desc->num_levels + 1);
+  t->desc.level_node_begin = t->levels.data();
+  std::memset(&t->stats, 0, sizeof t->stats);
+
+  auto cleanup = [&](int code, const std::string& what)
+  {
+    rt_free(t);
+    return fail(code, what);
+  };
+  cudaError_t e = cudaMalloc((void**)&t->d_blocks, desc->blocks_bytes ? desc->blocks_bytes : 16);
+  if (e != cudaSuccess)
+    return cleanup(RT_E_NOMEM, std::string("rt_upload: cudaMalloc(blocks): ") + cudaGetErrorString(e));
+  e = cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess)
+    return cleanup(RT_E_CUDA, std::string("rt_upload: stream: ") + cudaGetErrorString(e));
+  t->stream = t->own_stream;
+  for (int i = 0; i < EV_COUNT; ++i)
+  {
+    if ((e = cudaEventCreate(&t->ev[i])) != cudaSuccess)
+      return cleanup(RT_E_CUDA, std::string("rt_upload: event: ") + cudaGetErrorString(e));
+  }
+  if ((e = cudaEventCreate(&t->ev_t2_begin)) != cudaSuccess || (e = cudaEventCreate(&t->ev_t2_end)) != cudaSuccess)
+    return cleanup(RT_E_CUDA, std::string("rt_upload: event: ") + cudaGetErrorString(e));
+  e = cudaMemcpyAsync(t->d_blocks, desc->blocks, desc->blocks_bytes,
+                      desc->blocks_memory == RT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                      t->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(t->stream);
+  if (e != cudaSuccess)
+    return cleanup(RT_E_CUDA, std::string("rt_upload: copy of blocks: ") + cudaGetErrorString(e));
+  if ((e = t->d_counters.reserve(sizeof(Counters))) != cudaSuccess
+      || (e = t->h_counters.reserve(sizeof(Counters))) != cudaSuccess)
+    return cleanup(RT_E_NOMEM, std::string("rt_upload: counters: ") + cudaGetErrorString(e));
+
+  t->desc.blocks = t->d_blocks;
+  t->desc.blocks_memory = RT_MEM_DEVICE;
+  t->dev.blocks = t->d_blocks;
+  t->dev.leaf_offset = desc->leaf_offset;
+  t->dev.internal_stride = desc->internal_stride;
+  t->dev.leaf_stride = desc->leaf_stride;
+  t->dev.leaf_begin = t->levels[desc->leaf_level];
+  t->dev.num_nodes = desc->num_nodes;
+  t->dev.num_levels = desc->num_levels;
+  *out = t;
+  return RT_OK;
+}
+
+void rt_free(rt_tree* t)
+{
+  if (t == nullptr)
+    return;
+  cudaSetDevice(t->device);
+  if (t->own_stream)
+    cudaStreamSynchronize(t->own_stream);
+  DevBuf* dev[] = { &t->d_queries, &t->d_order, &t->d_counts, &t->d_offsets, &t->d_ids, &t->d_stash,
+                    &t->d_stash_pos, &t->d_deferred, &t->d_big, &t->d_scratch, &t->d_counters,
+                    &t->d_ray_t, &t->d_ray_id, &t->d_ray_any };
+  for (DevBuf* b : dev)
+    b->release();
+  HostBuf* host[] = { &t->h_counters, &t->h_offsets, &t->h_ids, &t->h_ray_t, &t->h_ray_id, &t->h_ray_any };
+  for (HostBuf* b : host)
+    b->release();
+  if (t->d_blocks)
+    cudaFree(t->d_blocks);
+  for (int i = 0; i < EV_COUNT; ++i)
+    if (t->ev[i])
+      cudaEventDestroy(t->ev[i]);
+  if (t->ev_t2_begin)
+    cudaEventDestroy(t->ev_t2_begin);
+  if (t->ev_t2_end)
+    cudaEventDestroy(t->ev_t2_end);
+  if (t->own_stream)
+    cudaStreamDestroy(t->own_stream);
+  cudaGetLastError();
+  delete t;
+}
+
+int rt_set_stream(rt_tree* t, void* cuda_stream)
+{
+  if (t == nullptr)
+    return fail(RT_E_INVALID, "rt_set_stream: tree is NULL");
+  t->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->own_stream;
+  return RT_OK;
+}
+
+int rt_get_stats(const rt_tree* t, rt_stats* out)
+{
+  if (t == nullptr || out == nullptr)
+    return fail(RT_E_INVALID, "rt_get_stats: NULL argument");
+  *out = t->stats;
+  return RT_OK;
+}
+
+int rt_tree_device_blocks(const rt_tree* t, void** device_ptr, uint64_t* bytes)
+{
+  if (t == nullptr || device_ptr == nullptr || bytes == nullptr)
+    return fail(RT_E_INVALID, "rt_tree_device_blocks: NULL argument");
+  *device_ptr = t->d_blocks;
+  *bytes = t->desc.blocks_bytes;
+  return RT_OK;
+}
+
+int rt_tree_get_desc(const rt_tree* t, rt_tree_desc* out)
+{
+  if (t == nullptr || out == nullptr)
+    return fail(RT_E_INVALID, "rt_tree_get_desc: NULL argument");
+  *out = t->desc;
+  return RT_OK;
+}
+
+int rt_query_boxes(rt_tree* t, const void* boxes, uint64_t n, uint32_t mode, uint32_t flags, rt_hits* out)
+{
+  if (t == nullptr || out == nullptr)
+    return fail(RT_E_INVALID, "rt_query_boxes: NULL argument");
+  if (boxes == nullptr && n > 0)
+    return fail(RT_E_INVALID, "rt_query_boxes: boxes is NULL");
+  if (mode > RT_CONTAINS)
+    return fail(RT_E_INVALID, "rt_query_boxes: unknown mode");
+  if (t->desc.key_kind == RT_KEY_BOX && mode == RT_POINT_IN_BOX)
+    return fail(RT_E_INVALID, "rt_query_boxes: RT_POINT_IN_BOX needs a point-keyed tree "
+                              "(use RT_INTERSECTS or RT_CONTAINS)");
+  if (n >= 0xFFFFFFFFull)
+    return fail(RT_E_INVALID, "rt_query_boxes: at most 2^32-2 queries per call");
+  rtb::box_launch_fn launch = rtb::find_box_kernel(t->desc.scalar, t->desc.dim, t->desc.width, t->desc.key_kind, mode);
+  if (launch == nullptr)
+    return fail(RT_E_UNSUPPORTED, "rt_query_boxes: no kernel for this tree");
+  int rc = use_device(t);
+  if (rc != RT_OK)
+    return rc;
+
+  std::memset(out, 0, sizeof *out);
+  std::memset(&t->stats, 0, sizeof t->stats);
+  cudaStream_t st = t->stream;
+  const uint32_t scalar_bytes = t->desc.scalar == RT_F64 ? 8u : 4u;
+  const size_t query_bytes = (size_t)n * 2 * t->desc.dim * scalar_bytes;
+  const bool on_device = (flags & RT_QUERIES_ON_DEVICE) != 0;
+  const bool keep_on_device = (flags & RT_RESULT_ON_DEVICE) != 0;
+  const bool count_only = (flags & RT_COUNT_ONLY) != 0;
+  const bool collect = (flags & RT_COLLECT_VISITS) != 0;
+  const bool sorted = (flags & RT_UNSORTED) == 0;
+  const bool reorder = (flags & RT_NO_REORDER) == 0 && n >= 4096;
+  const bool two_pass = collect || count_only;
+  uint32_t launches = 0;
+
+  // ---- buffers ---------------------------------------------------------------------
+  RT_CUDA(t->d_counts.reserve((size_t)(n + 4) * sizeof(uint32_t)));
+  RT_CUDA(t->d_offsets.reserve((size_t)(n + 1) * sizeof(unsigned long long)));
+  size_t scratch = rtb::scan_scratch_bytes(n);
+  if (reorder)
+    scratch = scratch > rtb::reorder_scratch_bytes(n) ? scratch : rtb::reorder_scratch_bytes(n);
+  RT_CUDA(t->d_scratch.reserve(scratch));
+  RT_CUDA(t->d_big.reserve((size_t)(n + 1) * sizeof(uint32_t)));
+  if (!on_device)
+    RT_CUDA(t->d_queries.reserve(query_bytes ? query_bytes : 16));
+  if (reorder)
+    RT_CUDA(t->d_order.reserve((size_t)n * sizeof(uint32_t)));
+  unsigned long long stash_capacity = 0;
+  if (!two_pass)
+  {
+    RT_CUDA(t->d_stash_pos.reserve((size_t)(n + 1) * sizeof(uint32_t)));
+    RT_CUDA(t->d_deferred.reserve((size_t)(n + 1) * sizeof(uint32_t)));
+    // pool: what the previous call needed (+25%), else ~12 ids per query; never more than a
+    // quarter of the free memory, never more than 32-bit positions can address
+    unsigned long long want = t->stash_wanted ? t->stash_wanted + t->stash_wanted / 4 : n * 12ull;
+    want += 4ull * rtb::STASH_SLAB * 1024;
+    if (want > 0xFFFFF000ull)
+      want = 0xFFFFF000ull;
+    const unsigned long long have = t->d_stash.cap / sizeof(uint32_t);
+    if (want > have)
+    {
+      // growing: cap the pool at a quarter of the free memory (cudaMemGetInfo costs
+      // milliseconds, so it is only asked when the pool really has to grow)
+      size_t free_b = 0, total_b = 0;
+      RT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      const unsigned long long limit = (unsigned long long)(free_b / 4 / sizeof(uint32_t)) + have;
+      if (want > limit)
+        want = limit;
+    }
+    if (want > have)
+    {
+      cudaError_t e = t->d_stash.reserve((size_t)want * sizeof(uint32_t));
+      if (e != cudaSuccess)
+        cudaGetLastError(); // keep whatever we have; overflowing queries are deferred
+    }
+    stash_capacity = t->d_stash.cap / sizeof(uint32_t);
+    if (stash_capacity > 0xFFFFF000ull)
+      stash_capacity = 0xFFFFF000ull;
+    // test knob: pretend the pool is this small so the exhaustion path can be exercised
+    if (const char* limit = std::getenv("RTB_STASH_LIMIT_IDS"))
+    {
+      const unsigned long long cap = std::strtoull(limit, nullptr, 10);
+      if (cap < stash_capacity)
+        stash_capacity = cap;
+    }
+  }
+
+  // ---- H2D ---------------------------------------------------------------------------
+  RT_CUDA(cudaEventRecord(t->ev[EV_BEGIN], st));
+  const void* d_q = boxes;
+  if (!on_device)
+  {
+    if (query_bytes)
+      RT_CUDA(cudaMemcpyAsync(t->d_queries.p, boxes, query_bytes, cudaMemcpyHostToDevice, st));
+    d_q = t->d_queries.p;
+  }
+  RT_CUDA(cudaMemsetAsync(t->d_counters.p, 0, sizeof(Counters), st));
+  RT_CUDA(cudaEventRecord(t->ev[EV_H2D], st));
+
+  // ---- coherence pass ----------------------------------------------------------------
+  const uint32_t* d_order = nullptr;
+  if (reorder)
+  {
+    RT_CUDA(rtb::launch_reorder(d_q, t->desc.scalar, t->desc.dim, 2 * t->desc.dim, n, t->d_order.as<uint32_t>(),
+                                t->d_scratch.p, st, &launches));
+    d_order = t->d_order.as<uint32_t>();
+  }
+  RT_CUDA(cudaEventRecord(t->ev[EV_REORDER], st));
+
+  // ---- first traversal -----------------------------------------------------------------
+  Counters* dc = t->d_counters.as<Counters>();
+  rtb::BoxLaunch L;
+  std::memset(&L, 0, sizeof L);
+  L.tree = t->dev;
+  L.queries = d_q;
+  L.order = d_order;
+  L.n = n;
+  L.counts = t->d_counts.as<uint32_t>();
+  L.offsets = t->d_offsets.as<unsigned long long>();
+  L.stash = t->d_stash.as<uint32_t>();
+  L.stash_pos = t->d_stash_pos.as<uint32_t>();
+  L.stash_capacity = stash_capacity;
+  L.stash_cursor = &dc->stash_cursor;
+  L.deferred_list = t->d_deferred.as<uint32_t>();
+  L.deferred_count = &dc->deferred;
+  L.big_list = t->d_big.as<uint32_t>();
+  L.big_count = &dc->big;
+  L.work_counter = &dc->work;
+  L.visit_stats = dc->visits;
+  L.sorted = sorted ? 1u : 0u;
+  L.stream = st;
+  L.pass = two_pass ? (collect ? rtb::PASS_COUNT_STATS : rtb::PASS_COUNT) : rtb::PASS_STASH;
+  if (n > 0)
+  {
+    RT_CUDA(launch(L));
+    ++launches;
+  }
+  RT_CUDA(cudaEventRecord(t->ev[EV_TRAVERSE], st));
+
+  // ---- CSR offsets, then the 64-byte read-back that sizes the id buffer -----------------
+  RT_CUDA(rtb::launch_exclusive_scan(t->d_counts.as<uint32_t>(), n, t->d_offsets.as<unsigned long long>(),
+                                     t->d_scratch.p, st, &launches));
+  RT_CUDA(cudaMemcpyAsync(&dc->total, t->d_offsets.as<unsigned long long>() + n, sizeof(unsigned long long),
+                          cudaMemcpyDeviceToDevice, st));
+  RT_CUDA(cudaMemcpyAsync(t->h_counters.p, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaStreamSynchronize(st));
+  Counters hc = *t->h_counters.as<Counters>();
+  const unsigned long long total = hc.total;
+  uint32_t deferred = 0;
+  if (!two_pass)
+    t->stash_wanted = hc.stash_cursor;
+
+  if (!count_only)
+  {
+    RT_CUDA(t->d_ids.reserve((size_t)(total ? total : 1) * sizeof(uint32_t)));
+    RT_CUDA(cudaEventRecord(t->ev_t2_begin, st));
+    bool second = false;
+    if (two_pass)
+    {
+      second = n > 0 && total > 0;
+      L.order = d_order;
+      L.n = n;
+      deferred = (uint32_t)n;
+    }
+    else
+    {
+      RT_CUDA(rtb::launch_gather_stash(t->d_stash.as<uint32_t>(), t->d_stash_pos.as<uint32_t>(),
+                                       t->d_offsets.as<unsigned long long>(), n, t->d_ids.as<uint32_t>(), st,
+                                       &launches));
+      deferred = hc.deferred;
+      second = deferred > 0;
+      L.order = t->d_deferred.as<uint32_t>();
+      L.n = deferred;
+    }
+    if (second)
+    {
+      RT_CUDA(cudaMemsetAsync(&dc->work, 0, sizeof(unsigned long long), st));
+      L.pass = rtb::PASS_WRITE;
+      L.ids = t->d_ids.as<uint32_t>();
+      RT_CUDA(launch(L));
+      ++launches;
+      if (sorted)
+        RT_CUDA(rtb::launch_sort_segments(t->d_big.as<uint32_t>(), &dc->big, (uint32_t)L.n,
+                                          t->d_offsets.as<unsigned long long>(), t->d_ids.as<uint32_t>(), st,
+                                          &launches));
+    }
+    RT_CUDA(cudaEventRecord(t->ev_t2_end, st));
+  }
+  RT_CUDA(cudaEventRecord(t->ev[EV_FINISH], st));
+
+  // ---- D2H ---------------------------------------------------------------------------------
+  out->n_queries = n;
+  out->total = total;
+  if (keep_on_device)
+  {
+    out->offsets = t->d_offsets.as<uint64_t>();
+    out->ids = count_only ? nullptr : t->d_ids.as<uint32_t>();
+    out->memory = RT_MEM_DEVICE;
+  }
+  else
+  {
+    RT_CUDA(t->h_offsets.reserve((size_t)(n + 1) * sizeof(unsigned long long)));
+    RT_CUDA(cudaMemcpyAsync(t->h_offsets.p, t->d_offsets.p, (size_t)(n + 1) * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, st));
+    if (!count_only)
+    {
+      RT_CUDA(t->h_ids.reserve((size_t)(total ? total : 1) * sizeof(uint32_t)));
+      if (total)
+        RT_CUDA(cudaMemcpyAsync(t->h_ids.p, t->d_ids.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    out->offsets = t->h_offsets.as<uint64_t>();
+    out->ids = count_only ? nullptr : t->h_ids.as<uint32_t>();
+    out->memory = RT_MEM_HOST;
+  }
+  RT_CUDA(cudaEventRecord(t->ev[EV_D2H], st));
+  RT_CUDA(cudaStreamSynchronize(st));
+
+  // ---- stats ---------------------------------------------------------------------------------
+  rt_stats& s = t->stats;
+  s.total_ms = elapsed(t->ev[EV_BEGIN], t->ev[EV_D2H]);
+  s.h2d_ms = elapsed(t->ev[EV_BEGIN], t->ev[EV_H2D]);
+  s.reorder_ms = elapsed(t->ev[EV_H2D], t->ev[EV_REORDER]);
+  s.traverse_ms = elapsed(t->ev[EV_REORDER], t->ev[EV_TRAVERSE]);
+  s.finish_ms = elapsed(t->ev[EV_TRAVERSE], t->ev[EV_FINISH]);
+  s.d2h_ms = elapsed(t->ev[EV_FINISH], t->ev[EV_D2H]);
+  s.kernel_launches = launches;
+  s.deferred_queries = count_only ? 0 : deferred;
+  if (collect)
+  {
+    s.visits_internal = hc.visits[0];
+    s.visits_leaf = hc.visits[1];
+    s.algorithmic_bytes = algorithmic_bytes_boxes(t, n, total, hc.visits[0], hc.visits[1]);
+  }
+  return RT_OK;
+}
+
+int rt_query_rays(rt_tree* t, const float* rays, uint64_t n, uint32_t mode, uint32_t flags, rt_ray_result* out)
+{
+  if (t == nullptr || out == nullptr)
+    return fail(RT_E_INVALID, "rt_query_rays: NULL argument");
+  if (rays == nullptr && n > 0)
+    return fail(RT_E_INVALID, "rt_query_rays: rays is NULL");
+  if (mode > RT_RAY_ANY)
+    return fail(RT_E_INVALID, "rt_query_rays: unknown mode");
+  if (t->desc.dim != 3 || t->desc.scalar != RT_F32)
+    return fail(RT_E_UNSUPPORTED, "rt_query_rays: ray queries need a 3-D float32 tree");
+  if (n >= 0xFFFFFFFFull)
+    return fail(RT_E_INVALID, "rt_query_rays: at most 2^32-2 rays per call");
+  int rc = use_device(t);
+  if (rc != RT_OK)
+    return rc;
+
+  std::memset(out, 0, sizeof *out);
+  std::memset(&t->stats, 0, sizeof t->stats);
+  cudaStream_t st = t->stream;
+  const size_t ray_bytes = (size_t)n * 7 * sizeof(float);
+  const bool on_device = (flags & RT_QUERIES_ON_DEVICE) != 0;
+  const bool keep_on_device = (flags & RT_RESULT_ON_DEVICE) != 0;
+  const bool count_only = (flags & RT_COUNT_ONLY) != 0;
+  const bool collect = (flags & RT_COLLECT_VISITS) != 0;
+  const bool sorted = (flags & RT_UNSORTED) == 0;
+  uint32_t launches = 0;
+
+  if (!on_device)
+    RT_CUDA(t->d_queries.reserve(ray_bytes ? ray_bytes : 16));
+  if (mode == RT_RAY_ALL_HITS)
+  {
+    RT_CUDA(t->d_counts.reserve((size_t)(n + 4) * sizeof(uint32_t)));
+    RT_CUDA(t->d_offsets.reserve((size_t)(n + 1) * sizeof(unsigned long long)));
+    RT_CUDA(t->d_scratch.reserve(rtb::scan_scratch_bytes(n)));
+    RT_CUDA(t->d_big.reserve((size_t)(n + 1) * sizeof(uint32_t)));
+  }
+  else if (mode == RT_RAY_CLOSEST)
+  {
+    RT_CUDA(t->d_ray_t.reserve((size_t)(n + 1) * sizeof(float)));
+    RT_CUDA(t->d_ray_id.reserve((size_t)(n + 1) * sizeof(uint32_t)));
+  }
+  else
+  {
+    RT_CUDA(t->d_ray_any.reserve((size_t)n + 16));
+  }
+
+  RT_CUDA(cudaEventRecord(t->ev[EV_BEGIN], st));
+  const float* d_rays = rays;
+  if (!on_device)
+  {
+    if (ray_bytes)
+      RT_CUDA(cudaMemcpyAsync(t->d_queries.p, rays, ray_bytes, cudaMemcpyHostToDevice, st));
+    d_rays = t->d_queries.as<float>();
+  }
+  RT_CUDA(cudaMemsetAsync(t->d_counters.p, 0, sizeof(Counters), st));
+  RT_CUDA(cudaEventRecord(t->ev[EV_H2D], st));
+  RT_CUDA(cudaEventRecord(t->ev[EV_REORDER], st));
+
+  Counters* dc = t->d_counters.as<Counters>();
+  rtb::RayLaunch L;
+  std::memset(&L, 0, sizeof L);
+  L.tree = t->dev;
+  L.width = t->desc.width;
+  L.key_kind = t->desc.key_kind;
+  L.rays = d_rays;
+  L.order = nullptr;
+  L.n = n;
+  L.mode = mode;
+  L.pass = collect ? rtb::PASS_COUNT_STATS : rtb::PASS_COUNT;
+  L.counts = t->d_counts.as<uint32_t>();
+  L.offsets = t->d_offsets.as<unsigned long long>();
+  L.big_list = t->d_big.as<uint32_t>();
+  L.big_count = &dc->big;
+  L.t_out = t->d_ray_t.as<float>();
+  L.id_out = t->d_ray_id.as<uint32_t>();
+  L.any_out = t->d_ray_any.as<uint8_t>();
+  L.work_counter = &dc->work;
+  L.visit_stats = dc->visits;
+  L.sorted = sorted ? 1u : 0u;
+  L.stream = st;
+  if (n > 0)
+  {
+    RT_CUDA(rtb::launch_ray_kernel(L));
+    ++launches;
+  }
+  RT_CUDA(cudaEventRecord(t->ev[EV_TRAVERSE], st));
+
+  Counters hc;
+  std::memset(&hc, 0, sizeof hc);
+  unsigned long long total = 0;
+  if (mode == RT_RAY_ALL_HITS)
+  {
+    RT_CUDA(rtb::launch_exclusive_scan(t->d_counts.as<uint32_t>(), n, t->d_offsets.as<unsigned long long>(),
+                                       t->d_scratch.p, st, &launches));
+    RT_CUDA(cudaMemcpyAsync(&dc->total, t->d_offsets.as<unsigned long long>() + n, sizeof(unsigned long long),
+                            cudaMemcpyDeviceToDevice, st));
+  }
+  RT_CUDA(cudaMemcpyAsync(t->h_counters.p, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaStreamSynchronize(st));
+  hc = *t->h_counters.as<Counters>();
+  total = hc.total;
+
+  if (mode == RT_RAY_ALL_HITS && !count_only)
+  {
+    RT_CUDA(t->d_ids.reserve((size_t)(total ? total : 1) * sizeof(uint32_t)));
+    if (n > 0 && total > 0)
+    {
+      RT_CUDA(cudaMemsetAsync(&dc->work, 0, sizeof(unsigned long long), st));
+      L.pass = rtb::PASS_WRITE;
+      L.ids = t->d_ids.as<uint32_t>();
+      RT_CUDA(rtb::launch_ray_kernel(L));
+      ++launches;
+      if (sorted)
+        RT_CUDA(rtb::launch_sort_segments(t->d_big.as<uint32_t>(), &dc->big, (uint32_t)n,
+                                          t->d_offsets.as<unsigned long long>(), t->d_ids.as<uint32_t>(), st,
+                                          &launches));
+    }
+  }
+  RT_CUDA(cudaEventRecord(t->ev[EV_FINISH], st));
+
+  out->n_rays = n;
+  out->memory = keep_on_device ? RT_MEM_DEVICE : RT_MEM_HOST;
+  if (mode == RT_RAY_ALL_HITS)
+  {
+    out->n_hit = total;
+    out->hits.n_queries = n;
+    out->hits.total = total;
+    out->hits.memory = out->memory;
+    if (keep_on_device)
+    {
+      out->hits.offsets = t->d_offsets.as<uint64_t>();
+      out->hits.ids = count_only ? nullptr : t->d_ids.as<uint32_t>();
+    }
+    else
+    {
+      RT_CUDA(t->h_offsets.reserve((size_t)(n + 1) * sizeof(unsigned long long)));
+      RT_CUDA(cudaMemcpyAsync(t->h_offsets.p, t->d_offsets.p, (size_t)(n + 1) * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, st));
+      if (!count_only)
+      {
+        RT_CUDA(t->h_ids.reserve((size_t)(total ? total : 1) * sizeof(uint32_t)));
+        if (total)
+          RT_CUDA(cudaMemcpyAsync(t->h_ids.p, t->d_ids.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                  st));
+      }
+      out->hits.offsets = t->h_offsets.as<uint64_t>();
+      out->hits.ids = count_only ? nullptr : t->h_ids.as<uint32_t>();
+    }
+  }
+  else if (mode == RT_RAY_CLOSEST)
+  {
+    out->n_hit = hc.visits[2];
+    if (keep_on_device)
+    {
+      out->t = t->d_ray_t.as<float>();
+      out->id = t->d_ray_id.as<uint32_t>();
+    }
+    else
+    {
+      RT_CUDA(t->h_ray_t.reserve((size_t)(n + 1) * sizeof(float)));
+      RT_CUDA(t->h_ray_id.reserve((size_t)(n + 1) * sizeof(uint32_t)));
+      if (n)
+      {
+        RT_CUDA(cudaMemcpyAsync(t->h_ray_t.p, t->d_ray_t.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        RT_CUDA(cudaMemcpyAsync(t->h_ray_id.p, t->d_ray_id.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      }
+      out->t = t->h_ray_t.as<float>();
+      out->id = t->h_ray_id.as<uint32_t>();
+    }
+  }
+  else
+  {
+    out->n_hit = hc.visits[2];
+    if (keep_on_device)
+    {
+      out->any = t->d_ray_any.as<uint8_t>();
+    }
+    else
+    {
+      RT_CUDA(t->h_ray_any.reserve((size_t)n + 16));
+      if (n)
+        RT_CUDA(cudaMemcpyAsync(t->h_ray_any.p, t->d_ray_any.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+      out->any = t->h_ray_any.as<uint8_t>();
+    }
+  }
+  RT_CUDA(cudaEventRecord(t->ev[EV_D2H], st));
+  RT_CUDA(cudaStreamSynchronize(st));
+
+  rt_stats& s = t->stats;
+  s.total_ms = elapsed(t->ev[EV_BEGIN], t->ev[EV_D2H]);
+  s.h2d_ms = elapsed(t->ev[EV_BEGIN], t->ev[EV_H2D]);
+  s.traverse_ms = elapsed(t->ev[EV_REORDER], t->ev[EV_TRAVERSE]);
+  s.finish_ms = elapsed(t->ev[EV_TRAVERSE], t->ev[EV_FINISH]);
+  s.d2h_ms = elapsed(t->ev[EV_FINISH], t->ev[EV_D2H]);
+  s.kernel_launches = launches;
+  if (collect && mode == RT_RAY_ALL_HITS)
+  {
+    s.visits_internal = hc.visits[0];
+    s.visits_leaf = hc.visits[1];
+    const uint64_t M = t->desc.max_entries;
+    const uint64_t b_int = M * (2 * 3 * 4 + 4);
+    const uint64_t b_leaf = t->desc.key_kind == RT_KEY_BOX ? b_int : M * (3 * 4 + 4);
+    s.algorithmic_bytes = hc.visits[0] * b_int + hc.visits[1] * b_leaf + n * (28 + 8) + 4 * total;
+  }
+  return RT_OK;
+}
+
+} // extern "C"
+
+namespace rtb
+{
+box_launch_fn find_box_kernel(uint32_t scalar, uint32_t dim, uint32_t width, uint32_t key_kind, uint32_t mode)
+{
+  switch (scalar)
+  {
+  case RT_F32: return find_box_kernel_f32(dim, width, key_kind, mode);
+  case RT_F64: return find_box_kernel_f64(dim, width, key_kind, mode);
+  case RT_I32: return find_box_kernel_i32(dim, width, key_kind, mode);
+  default: return nullptr;
+  }
+}
+} // namespace rtb

@@ -1,0 +1,126 @@
+// rt_common.cuh -- shared declarations of the sm_100a query engine (internal header).
+//
+// Division of labour inside librtree_b200.so:
+//   rt_api.cu          C ABI, device buffers, streams / events, the per-call pipeline
+//   rt_box_*.cu        instantiations of the box traversal kernel (rt_traverse_box.cuh)
+//   rt_ray.cu          the ray traversal kernels (rt_traverse_ray.cuh)
+//   rt_passes.cu       hand-written scan, gather, segment sort and query reordering
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include <rtree_b200.h>
+
+namespace rtb
+{
+
+// The uploaded tree as kernels see it (see rt_tree_desc in include/rtree_b200.h).
+struct TreeDev
+{
+  const unsigned char* blocks; // internal blocks, then (at leaf_offset) leaf blocks
+  unsigned long long leaf_offset;
+  uint32_t internal_stride;
+  uint32_t leaf_stride;
+  uint32_t leaf_begin; // first leaf node index == number of internal nodes
+  uint32_t num_nodes;
+  uint32_t num_levels;
+};
+
+// traversal passes
+enum : uint32_t
+{
+  PASS_COUNT = 0,       // counts[q] only
+  PASS_COUNT_STATS = 1, // counts[q] + node-visit totals (RT_COLLECT_VISITS)
+  PASS_STASH = 2,       // counts[q]; sorted hit lists of <= HIT_BUF hits go to the stash
+  PASS_WRITE = 3        // hits go to ids[offsets[q] ...), small lists sorted in the warp
+};
+
+constexpr uint32_t HIT_BUF = 32;        // per-warp hit buffer (one id per lane)
+constexpr uint32_t STASH_SLAB = 512;    // ids a warp reserves from the stash per atomic
+constexpr uint32_t NO_STASH = 0xFFFFFFFFu;
+constexpr int TRAVERSE_THREADS = 256;   // 8 warps per CTA
+constexpr uint32_t QUERY_CHUNK = 8;     // queries a warp claims per atomic
+
+struct BoxLaunch
+{
+  TreeDev tree;
+  const void* queries;      // [n][2][dim] scalars (device)
+  const uint32_t* order;    // nullable: i-th processed query is order[i]
+  uint64_t n;               // number of queries to process (length of order if given)
+  uint32_t pass;
+  // outputs / inputs by pass
+  uint32_t* counts;                 // [n_total] hits per query (COUNT*, STASH)
+  const unsigned long long* offsets; // [n_total+1] (WRITE)
+  uint32_t* ids;                    // [total]     (WRITE)
+  uint32_t* stash;                  // stash pool  (STASH)
+  uint32_t* stash_pos;              // [n_total] position in the pool or NO_STASH (STASH)
+  unsigned long long stash_capacity;
+  unsigned long long* stash_cursor; // device counter
+  uint32_t* deferred_list;          // queries that need PASS_WRITE (STASH)
+  uint32_t* deferred_count;
+  uint32_t* big_list;               // queries whose list must be sorted afterwards (WRITE)
+  uint32_t* big_count;
+  unsigned long long* work_counter; // device counter, zeroed before launch
+  unsigned long long* visit_stats;  // [2] internal / leaf visits (COUNT_STATS)
+  uint32_t sorted;                  // 0: keep traversal order
+  int grid;                         // 0: pick from occupancy
+  cudaStream_t stream;
+};
+
+typedef cudaError_t (*box_launch_fn)(const BoxLaunch&);
+
+// rt_box_*.cu: nullptr when the combination is not instantiated
+box_launch_fn find_box_kernel(uint32_t scalar, uint32_t dim, uint32_t width, uint32_t key_kind,
+                              uint32_t mode);
+box_launch_fn find_box_kernel_f32(uint32_t dim, uint32_t width, uint32_t key_kind, uint32_t mode);
+box_launch_fn find_box_kernel_f64(uint32_t dim, uint32_t width, uint32_t key_kind, uint32_t mode);
+box_launch_fn find_box_kernel_i32(uint32_t dim, uint32_t width, uint32_t key_kind, uint32_t mode);
+
+struct RayLaunch
+{
+  TreeDev tree;
+  uint32_t width;
+  uint32_t key_kind;
+  const float* rays;     // [n][7]
+  const uint32_t* order;
+  uint64_t n;
+  uint32_t mode;         // RT_RAY_*
+  uint32_t pass;         // PASS_COUNT / PASS_COUNT_STATS / PASS_WRITE for ALL_HITS; ignored otherwise
+  uint32_t* counts;
+  const unsigned long long* offsets;
+  uint32_t* ids;
+  uint32_t* big_list;
+  uint32_t* big_count;
+  float* t_out;
+  uint32_t* id_out;
+  uint8_t* any_out;
+  unsigned long long* work_counter;
+  unsigned long long* visit_stats;
+  uint32_t sorted;
+  int grid;
+  cudaStream_t stream;
+};
+cudaError_t launch_ray_kernel(const RayLaunch&); // rt_ray.cu; cudaErrorInvalidValue if unsupported
+
+// ---- rt_passes.cu -----------------------------------------------------------------
+// offsets[0..n] = exclusive prefix sum of counts[0..n) (64-bit); scratch >= scan_scratch_bytes(n)
+size_t scan_scratch_bytes(uint64_t n);
+cudaError_t launch_exclusive_scan(const uint32_t* counts, uint64_t n, unsigned long long* offsets,
+                                  void* scratch, cudaStream_t stream, uint32_t* launches);
+// ids[offsets[q] + k] = stash[stash_pos[q] + k] for every stashed query
+cudaError_t launch_gather_stash(const uint32_t* stash, const uint32_t* stash_pos,
+                                const unsigned long long* offsets, uint64_t n, uint32_t* ids,
+                                cudaStream_t stream, uint32_t* launches);
+// sort ids[offsets[q] .. offsets[q+1]) ascending for the queries in big_list
+cudaError_t launch_sort_segments(const uint32_t* big_list, const uint32_t* big_count_dev,
+                                 uint32_t max_segments, const unsigned long long* offsets,
+                                 uint32_t* ids, cudaStream_t stream, uint32_t* launches);
+// coherence pass: order[] = query indices grouped by the Morton cell of the box centre
+// (first 3 axes), cells sized from the batch's own extent; scratch >= reorder_scratch_bytes()
+size_t reorder_scratch_bytes(uint64_t n);
+cudaError_t launch_reorder(const void* queries, uint32_t scalar, uint32_t dim, uint32_t floats_per_query,
+                           uint64_t n, uint32_t* order, void* scratch, cudaStream_t stream,
+                           uint32_t* launches);
+
+} // namespace rtb

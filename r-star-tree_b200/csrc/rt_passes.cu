@@ -1,0 +1,462 @@
+// rt_passes.cu -- the small passes around the traversal kernels (hand-written, sm_100a):
+//   * 64-bit exclusive scan of the per-query hit counts  -> CSR offsets
+//   * gather of the stashed (already sorted) hit lists to their CSR position
+//   * ascending sort of the long hit lists the traversal could not sort in a warp
+//   * query reordering by Morton cell (coherence pass)
+// All are bandwidth-trivial next to the traversal (a few bytes per query).
+#include "rt_common.cuh"
+
+namespace rtb
+{
+
+// ================================ exclusive scan ====================================
+namespace
+{
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ unsigned long long warp_inclusive(unsigned long long v, int lane)
+{
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1)
+  {
+    const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, v, d);
+    if (lane >= d)
+      v += up;
+  }
+  return v;
+}
+
+// inclusive scan of one value per thread across the block; returns the block total via *total
+__device__ __forceinline__ unsigned long long block_inclusive(unsigned long long v, unsigned long long* warp_sums,
+                                                              unsigned long long* total)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_inclusive(v, lane);
+  if (lane == 31)
+    warp_sums[warp] = v;
+  __syncthreads();
+  if (warp == 0)
+  {
+    unsigned long long s = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0ull;
+    s = warp_inclusive(s, lane);
+    warp_sums[lane] = s;
+  }
+  __syncthreads();
+  if (warp > 0)
+    v += warp_sums[warp - 1];
+  *total = warp_sums[(blockDim.x >> 5) - 1];
+  return v;
+}
+
+__device__ __forceinline__ void load_tile(const uint32_t* counts, uint64_t n, uint64_t base, uint32_t (&x)[SCAN_ITEMS])
+{
+  if (base + SCAN_ITEMS <= n)
+  {
+    const uint4 v = *reinterpret_cast<const uint4*>(counts + base);
+    x[0] = v.x, x[1] = v.y, x[2] = v.z, x[3] = v.w;
+  }
+  else
+  {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+      x[k] = (base + k < n) ? counts[base + k] : 0u;
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const uint32_t* counts, uint64_t n,
+                                                               unsigned long long* tile_sums)
+{
+  __shared__ unsigned long long warp_sums[32];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t x[SCAN_ITEMS];
+  load_tile(counts, n, base, x);
+  unsigned long long total;
+  block_inclusive((unsigned long long)x[0] + x[1] + x[2] + x[3], warp_sums, &total);
+  if (threadIdx.x == 0)
+    tile_sums[blockIdx.x] = total;
+}
+
+// one block: exclusive scan of the tile sums in place, carrying across chunks
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_offsets(unsigned long long* tile_sums, uint64_t tiles)
+{
+  __shared__ unsigned long long warp_sums[32];
+  unsigned long long carry = 0;
+  for (uint64_t base = 0; base < tiles; base += SCAN_THREADS)
+  {
+    const uint64_t i = base + threadIdx.x;
+    const unsigned long long v = (i < tiles) ? tile_sums[i] : 0ull;
+    unsigned long long total;
+    const unsigned long long inc = block_inclusive(v, warp_sums, &total);
+    if (i < tiles)
+      tile_sums[i] = carry + inc - v;
+    carry += total;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_write_offsets(const uint32_t* counts, uint64_t n,
+                                                                   const unsigned long long* tile_offsets,
+                                                                   unsigned long long* offsets)
+{
+  __shared__ unsigned long long warp_sums[32];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t x[SCAN_ITEMS];
+  load_tile(counts, n, base, x);
+  const unsigned long long mine = (unsigned long long)x[0] + x[1] + x[2] + x[3];
+  unsigned long long total;
+  const unsigned long long inc = block_inclusive(mine, warp_sums, &total);
+  unsigned long long run = tile_offsets[blockIdx.x] + inc - mine;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k)
+  {
+    if (base + k < n)
+      offsets[base + k] = run;
+    run += x[k];
+    if (base + k + 1 == n)
+      offsets[n] = run;
+  }
+}
+
+__global__ void scan_empty(unsigned long long* offsets) { offsets[0] = 0; }
+} // namespace
+
+size_t scan_scratch_bytes(uint64_t n)
+{
+  const uint64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  return (size_t)(tiles + 1) * sizeof(unsigned long long);
+}
+
+cudaError_t launch_exclusive_scan(const uint32_t* counts, uint64_t n, unsigned long long* offsets,
+                                  void* scratch, cudaStream_t stream, uint32_t* launches)
+{
+  if (n == 0)
+  {
+    scan_empty<<<1, 1, 0, stream>>>(offsets);
+    *launches += 1;
+    return cudaGetLastError();
+  }
+  const uint64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  unsigned long long* tile_sums = static_cast<unsigned long long*>(scratch);
+  scan_tile_sums<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(counts, n, tile_sums);
+  scan_tile_offsets<<<1, SCAN_THREADS, 0, stream>>>(tile_sums, tiles);
+  scan_write_offsets<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(counts, n, tile_sums, offsets);
+  *launches += 3;
+  return cudaGetLastError();
+}
+
+// ================================ stash gather ======================================
+namespace
+{
+// 8 lanes per query: the common list (about 10 ids) moves in two coalesced steps
+__global__ void __launch_bounds__(256) gather_stash_kernel(const uint32_t* __restrict__ stash,
+                                                           const uint32_t* __restrict__ stash_pos,
+                                                           const unsigned long long* __restrict__ offsets,
+                                                           uint64_t n, uint32_t* __restrict__ ids)
+{
+  const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const uint32_t sub = threadIdx.x & 7;
+  if (q >= n)
+    return;
+  const uint32_t from = stash_pos[q];
+  if (from == NO_STASH)
+    return;
+  const unsigned long long begin = offsets[q];
+  const uint32_t count = (uint32_t)(offsets[q + 1] - begin);
+  for (uint32_t k = sub; k < count; k += 8)
+    ids[begin + k] = stash[(unsigned long long)from + k];
+}
+} // namespace
+
+cudaError_t launch_gather_stash(const uint32_t* stash, const uint32_t* stash_pos,
+                                const unsigned long long* offsets, uint64_t n, uint32_t* ids,
+                                cudaStream_t stream, uint32_t* launches)
+{
+  if (n == 0)
+    return cudaSuccess;
+  const uint64_t threads = n * 8;
+  const uint64_t blocks = (threads + 255) / 256;
+  gather_stash_kernel<<<(unsigned)blocks, 256, 0, stream>>>(stash, stash_pos, offsets, n, ids);
+  *launches += 1;
+  return cudaGetLastError();
+}
+
+// ================================ segment sort ======================================
+namespace
+{
+constexpr int SORT_THREADS = 512;
+constexpr uint32_t SORT_SMEM_IDS = 8192;
+
+// Bitonic network with every comparison ascending (mirror partner on the first step of a
+// merge), so indices >= len act as +infinity padding and never need to exist.
+__device__ void bitonic_ascending(uint32_t* a, uint64_t len)
+{
+  uint64_t padded = 1;
+  while (padded < len)
+    padded <<= 1;
+  for (uint64_t k = 2; k <= padded; k <<= 1)
+  {
+    for (uint64_t j = k >> 1; j > 0; j >>= 1)
+    {
+      for (uint64_t i = threadIdx.x; i < len; i += blockDim.x)
+      {
+        const uint64_t partner = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+        if (partner > i && partner < len)
+        {
+          const uint32_t x = a[i], y = a[partner];
+          if (x > y)
+          {
+            a[i] = y;
+            a[partner] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) sort_segments_kernel(const uint32_t* __restrict__ big_list,
+                                                                     const uint32_t* __restrict__ big_count,
+                                                                     const unsigned long long* __restrict__ offsets,
+                                                                     uint32_t* ids)
+{
+  __shared__ uint32_t buf[SORT_SMEM_IDS];
+  const uint32_t segments = *big_count;
+  for (uint32_t s = blockIdx.x; s < segments; s += gridDim.x)
+  {
+    const uint32_t q = big_list[s];
+    const unsigned long long begin = offsets[q];
+    const uint64_t len = offsets[q + 1] - begin;
+    uint32_t* seg = ids + begin;
+    if (len <= SORT_SMEM_IDS)
+    {
+      for (uint64_t i = threadIdx.x; i < len; i += blockDim.x)
+        buf[i] = seg[i];
+      __syncthreads();
+      bitonic_ascending(buf, len);
+      for (uint64_t i = threadIdx.x; i < len; i += blockDim.x)
+        seg[i] = buf[i];
+      __syncthreads();
+    }
+    else
+    {
+      __syncthreads();
+      bitonic_ascending(seg, len); // in global memory; __syncthreads orders the block's accesses
+      __syncthreads();
+    }
+  }
+}
+} // namespace
+
+cudaError_t launch_sort_segments(const uint32_t* big_list, const uint32_t* big_count_dev,
+                                 uint32_t max_segments, const unsigned long long* offsets,
+                                 uint32_t* ids, cudaStream_t stream, uint32_t* launches)
+{
+  if (max_segments == 0)
+    return cudaSuccess;
+  const unsigned grid = max_segments < 148u * 4u ? max_segments : 148u * 4u;
+  sort_segments_kernel<<<grid, SORT_THREADS, 0, stream>>>(big_list, big_count_dev, offsets, ids);
+  *launches += 1;
+  return cudaGetLastError();
+}
+
+// ================================ query reordering ==================================
+// Counting sort of the queries by the Morton cell of their box centre.  Which query a warp
+// works on next then shares most of its root-to-leaf path with the previous one, so node
+// blocks are found in L1/L2 instead of HBM.  Results are written by ORIGINAL query index,
+// so the order inside a cell (decided by atomics) never shows in the output.
+namespace
+{
+constexpr uint32_t CELL_BITS_PER_AXIS = 7;                       // 128 cells per axis
+constexpr uint32_t CELL_COUNT = 1u << (3 * CELL_BITS_PER_AXIS);  // 2 M cells
+
+template <typename S>
+__device__ __forceinline__ float centre_of(const S* q, uint32_t dim, uint32_t axis)
+{
+  return 0.5f * ((float)q[axis] + (float)q[dim + axis]);
+}
+
+__device__ __forceinline__ uint32_t spread3(uint32_t v)
+{
+  v &= 0x3FFu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+// order-preserving float <-> uint mapping for atomicMin/Max
+__device__ __forceinline__ uint32_t float_key(float f)
+{
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k)
+{
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+struct ReorderScratch
+{
+  uint32_t ext_min[3];
+  uint32_t ext_max[3];
+};
+
+__global__ void reorder_init(ReorderScratch* s, uint32_t* cell_count)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3)
+  {
+    s->ext_min[i] = 0xFFFFFFFFu;
+    s->ext_max[i] = 0u;
+  }
+  for (uint32_t c = i; c <= CELL_COUNT; c += gridDim.x * blockDim.x)
+    cell_count[c] = 0;
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256) reorder_extent(const S* __restrict__ q, uint32_t dim, uint32_t stride,
+                                                      uint64_t n, ReorderScratch* s)
+{
+  const uint32_t axes = dim < 3 ? dim : 3;
+  float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+  {
+    for (uint32_t a = 0; a < axes; ++a)
+    {
+      const float c = centre_of(q + i * stride, dim, a);
+      if (c == c && fabsf(c) != INFINITY)
+      {
+        lo[a] = fminf(lo[a], c);
+        hi[a] = fmaxf(hi[a], c);
+      }
+    }
+  }
+  for (uint32_t a = 0; a < axes; ++a)
+  {
+    for (int d = 16; d > 0; d >>= 1)
+    {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], d));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], d));
+    }
+    if ((threadIdx.x & 31) == 0 && lo[a] <= hi[a])
+    {
+      atomicMin(&s->ext_min[a], float_key(lo[a]));
+      atomicMax(&s->ext_max[a], float_key(hi[a]));
+    }
+  }
+}
+
+template <typename S>
+__device__ __forceinline__ uint32_t cell_of(const S* q, uint32_t dim, const ReorderScratch* s)
+{
+  const uint32_t axes = dim < 3 ? dim : 3;
+  uint32_t code = 0;
+  for (uint32_t a = 0; a < axes; ++a)
+  {
+    const float lo = key_float(s->ext_min[a]), hi = key_float(s->ext_max[a]);
+    const float c = centre_of(q, dim, a);
+    float t = (hi > lo) ? (c - lo) / (hi - lo) : 0.0f;
+    t = (t == t) ? fminf(fmaxf(t, 0.0f), 1.0f) : 0.0f;
+    const uint32_t cell = min((uint32_t)(t * (float)(1u << CELL_BITS_PER_AXIS)), (1u << CELL_BITS_PER_AXIS) - 1u);
+    code |= spread3(cell) << a;
+  }
+  return code;
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256) reorder_histogram(const S* __restrict__ q, uint32_t dim, uint32_t stride,
+                                                         uint64_t n, const ReorderScratch* s,
+                                                         uint32_t* cell_count, uint32_t* cell_of_query)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const uint32_t c = cell_of(q + i * stride, dim, s);
+    cell_of_query[i] = c;
+    atomicAdd(&cell_count[c], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256) reorder_scatter(const uint32_t* __restrict__ cell_of_query, uint64_t n,
+                                                       const unsigned long long* __restrict__ cell_begin,
+                                                       uint32_t* cell_fill, uint32_t* order)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const uint32_t c = cell_of_query[i];
+    const uint32_t k = atomicAdd(&cell_fill[c], 1u);
+    order[cell_begin[c] + k] = (uint32_t)i;
+  }
+}
+
+__global__ void zero_u32(uint32_t* p, uint32_t n)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    p[i] = 0;
+}
+} // namespace
+
+// scratch layout: ReorderScratch | cell_count[CELL_COUNT+1] u32 | cell_begin[CELL_COUNT+2] u64 |
+//                 scan scratch | cell_of_query[n] u32
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+size_t reorder_scratch_bytes(uint64_t n)
+{
+  return align256(sizeof(ReorderScratch)) + align256((CELL_COUNT + 1) * sizeof(uint32_t))
+         + align256((CELL_COUNT + 2) * sizeof(unsigned long long)) + align256(scan_scratch_bytes(CELL_COUNT + 1))
+         + align256(n * sizeof(uint32_t));
+}
+
+cudaError_t launch_reorder(const void* queries, uint32_t scalar, uint32_t dim, uint32_t scalars_per_query,
+                           uint64_t n, uint32_t* order, void* scratch, cudaStream_t stream,
+                           uint32_t* launches)
+{
+  if (n == 0)
+    return cudaSuccess;
+  unsigned char* base = static_cast<unsigned char*>(scratch);
+  ReorderScratch* rs = reinterpret_cast<ReorderScratch*>(base);
+  base += align256(sizeof(ReorderScratch));
+  uint32_t* cell_count = reinterpret_cast<uint32_t*>(base);
+  base += align256((CELL_COUNT + 1) * sizeof(uint32_t));
+  unsigned long long* cell_begin = reinterpret_cast<unsigned long long*>(base);
+  base += align256((CELL_COUNT + 2) * sizeof(unsigned long long));
+  void* scan_scratch = base;
+  base += align256(scan_scratch_bytes(CELL_COUNT + 1));
+  uint32_t* cell_of_query = reinterpret_cast<uint32_t*>(base);
+
+  const unsigned grid = 148 * 8;
+  reorder_init<<<grid, 256, 0, stream>>>(rs, cell_count);
+  *launches += 1;
+  switch (scalar)
+  {
+  case RT_F32:
+    reorder_extent<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(queries), dim, scalars_per_query, n, rs);
+    reorder_histogram<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(queries), dim, scalars_per_query, n,
+                                                       rs, cell_count, cell_of_query);
+    break;
+  case RT_F64:
+    reorder_extent<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(queries), dim, scalars_per_query, n, rs);
+    reorder_histogram<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(queries), dim, scalars_per_query,
+                                                        n, rs, cell_count, cell_of_query);
+    break;
+  case RT_I32:
+    reorder_extent<int32_t><<<grid, 256, 0, stream>>>(static_cast<const int32_t*>(queries), dim, scalars_per_query, n, rs);
+    reorder_histogram<int32_t><<<grid, 256, 0, stream>>>(static_cast<const int32_t*>(queries), dim, scalars_per_query,
+                                                         n, rs, cell_count, cell_of_query);
+    break;
+  default: return cudaErrorInvalidValue;
+  }
+  *launches += 2;
+  cudaError_t err = launch_exclusive_scan(cell_count, CELL_COUNT + 1, cell_begin, scan_scratch, stream, launches);
+  if (err != cudaSuccess)
+    return err;
+  zero_u32<<<grid, 256, 0, stream>>>(cell_count, CELL_COUNT + 1);
+  reorder_scatter<<<grid, 256, 0, stream>>>(cell_of_query, n, cell_begin, cell_count, order);
+  *launches += 2;
+  return cudaGetLastError();
+}
+
+} // namespace rtb

@@ -1,0 +1,356 @@
+// rt_traverse_box.cuh -- the hot kernel: warp-cooperative AABB range queries (sm_100a).
+//
+// Replaces a host loop over RTree::search(filter, functor) (reference
+// include/RTree/rtree.hpp:1141-1146; recursion :984-1019) with
+//   filter  = closed overlap of the child bound with the query box
+//             (reference example/sample/sample.cpp:48-54, test/rtree.cpp:403)
+//   functor = is_inside(query box, key)   (reference include/RTree/aabb.hpp:206-210,
+//             less_equal :249-259; flat form: test/rtree.cpp:390)
+// on the level-ordered SoA blocks of RTree::flatten_device().
+//
+// Mapping.  One warp answers one query at a time.  A block is W (8 or 16) slots wide, so
+// the 32 lanes cover G = 32/W nodes per step: lane = (group g, slot c) loads child c of
+// the g-th node popped from the warp's stack -- one 4/8-byte load per row, the W lanes of
+// a group reading one contiguous, sector-aligned row (SoA), i.e. fully coalesced.  The
+// per-axis interval tests run in registers, __ballot_sync gathers the W-bit hit masks of
+// all G nodes at once, and __popc over the lower lanes gives every hit lane its slot on
+// the stack (children to descend) or in the hit list (leaf entries), so both compactions
+// are branch-free and deterministic.
+//
+// Stack.  Per warp in shared memory.  Popping the top G entries and pushing children in
+// lane order keeps the stack sorted by level, hence at most 32 entries per level are
+// ever live: capacity 32 * num_levels, no overflow path needed.
+//
+// Memory.  Internal levels are a small, hot prefix of the block buffer; they and the
+// leaves stream through L1/L2 via the read-only path (ld.global.nc).  Nothing is written
+// but counts / hit ids.
+//
+// Output.  PASS_COUNT(+STATS): hits per query.  PASS_STASH: hits per query, and lists of
+// at most HIT_BUF hits are sorted in registers (bitonic over the warp) and parked in a
+// stash so that the second traversal is only needed for the rare longer lists.
+// PASS_WRITE: hit ids go to their final CSR position; short lists are sorted in the warp.
+#pragma once
+
+#include "rt_common.cuh"
+
+namespace rtb
+{
+
+template <typename S>
+__device__ __forceinline__ S ld_ro(const S* p)
+{
+  return __ldg(p);
+}
+
+// ascending bitonic sort of one value per lane
+__device__ __forceinline__ uint32_t warp_sort32(uint32_t v, int lane)
+{
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1)
+  {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1)
+    {
+      const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, v, j);
+      const bool ascending = (lane & k) == 0;
+      const bool lower = (lane & j) == 0;
+      v = (lower == ascending) ? min(v, other) : max(v, other);
+    }
+  }
+  return v;
+}
+
+template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS>
+__global__ void __launch_bounds__(TRAVERSE_THREADS)
+box_traverse_kernel(const BoxLaunch p)
+{
+  constexpr int G = 32 / W;
+  extern __shared__ uint32_t smem[];
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int slot = lane % W;
+  const int grp = lane / W;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  const uint32_t stack_cap = 32u * p.tree.num_levels;
+  uint32_t* stack = smem + warp * (stack_cap + HIT_BUF);
+  uint32_t* hitbuf = stack + stack_cap;
+
+  const unsigned char* __restrict__ int_base = p.tree.blocks;
+  const unsigned char* __restrict__ leaf_base = p.tree.blocks + p.tree.leaf_offset;
+  const uint32_t leaf_begin = p.tree.leaf_begin;
+  const uint32_t int_stride = p.tree.internal_stride;
+  const uint32_t leaf_stride = p.tree.leaf_stride;
+  constexpr uint32_t LINK_OFF_INTERNAL = 2u * D * W * sizeof(S);
+  constexpr uint32_t LINK_OFF_LEAF = (BOXKEY ? 2u : 1u) * D * W * sizeof(S);
+
+  const S* __restrict__ queries = static_cast<const S*>(p.queries);
+
+  unsigned long long visits_int = 0, visits_leaf = 0;
+  // stash slab owned by this warp (PASS_STASH)
+  unsigned long long slab_pos = 0;
+  uint32_t slab_left = 0;
+
+  for (;;)
+  {
+    unsigned long long first = 0;
+    if (lane == 0)
+      first = atomicAdd(p.work_counter, (unsigned long long)QUERY_CHUNK);
+    first = __shfl_sync(0xFFFFFFFFu, first, 0);
+    if (first >= p.n)
+      break;
+    const unsigned long long last = min(first + (unsigned long long)QUERY_CHUNK, (unsigned long long)p.n);
+
+    for (unsigned long long i = first; i < last; ++i)
+    {
+      const unsigned long long qi = p.order ? (unsigned long long)p.order[i] : i;
+      S qlo[D], qhi[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+      {
+        qlo[d] = ld_ro(queries + qi * (2 * D) + d);
+        qhi[d] = ld_ro(queries + qi * (2 * D) + D + d);
+      }
+
+      unsigned long long out_base = 0;
+      uint32_t expect = 0;
+      bool buffered = (PASS == PASS_STASH);
+      if (PASS == PASS_WRITE)
+      {
+        out_base = p.offsets[qi];
+        expect = (uint32_t)min(p.offsets[qi + 1] - out_base, (unsigned long long)0xFFFFFFFFu);
+        buffered = p.sorted && expect <= HIT_BUF;
+      }
+
+      uint32_t count = 0;
+      uint32_t sp = 1;
+      if (lane == 0)
+        stack[0] = 0; // the root; its own bound is never tested (reference rtree.hpp:984)
+      __syncwarp();
+
+      while (sp > 0)
+      {
+        const uint32_t take = min(sp, (uint32_t)G);
+        sp -= take;
+        const bool active = (uint32_t)grp < take;
+        uint32_t node = RT_INVALID_ID;
+        if (active)
+          node = stack[sp + grp];
+        __syncwarp();
+
+        const bool is_leaf = node >= leaf_begin;
+        const unsigned char* blk = is_leaf
+                                       ? leaf_base + (unsigned long long)(node - leaf_begin) * leaf_stride
+                                       : int_base + (unsigned long long)node * int_stride;
+        const bool one_corner = !BOXKEY && is_leaf;
+
+        uint32_t link = RT_INVALID_ID;
+        bool hit = false;
+        if (active)
+        {
+          const S* row = reinterpret_cast<const S*>(blk) + slot;
+          link = ld_ro(reinterpret_cast<const uint32_t*>(blk + (is_leaf ? LINK_OFF_LEAF : LINK_OFF_INTERNAL)) + slot);
+          S lo[D], hi[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d)
+            lo[d] = ld_ro(row + d * W);
+#pragma unroll
+          for (int d = 0; d < D; ++d)
+            hi[d] = one_corner ? lo[d] : ld_ro(row + (D + d) * W);
+          hit = link != RT_INVALID_ID;
+#pragma unroll
+          for (int d = 0; d < D; ++d)
+          {
+            if (BOXKEY && CONTAINS)
+            {
+              // leaf: key box inside the query box; internal: closed overlap
+              const S a = is_leaf ? lo[d] : hi[d];
+              const S b = is_leaf ? hi[d] : lo[d];
+              hit = hit && !(a < qlo[d]) && !(b > qhi[d]);
+            }
+            else
+            {
+              // closed overlap; for a point key (lo == hi) this IS the reference's
+              // is_inside: !(p < qmin) && !(p > qmax) per axis
+              hit = hit && !(hi[d] < qlo[d]) && !(lo[d] > qhi[d]);
+            }
+          }
+        }
+
+        const uint32_t m_all = __ballot_sync(0xFFFFFFFFu, hit);
+        const uint32_t m_leaf = __ballot_sync(0xFFFFFFFFu, hit && is_leaf);
+        const uint32_t m_int = m_all & ~m_leaf;
+
+        if (PASS == PASS_COUNT_STATS)
+        {
+          const uint32_t leaf_nodes = __popc(__ballot_sync(0xFFFFFFFFu, active && is_leaf && slot == 0));
+          visits_leaf += leaf_nodes;
+          visits_int += take - leaf_nodes;
+        }
+
+        // children to descend: compact onto the stack in lane order (keeps it level-sorted)
+        if (hit && !is_leaf)
+          stack[sp + __popc(m_int & lt_mask)] = link;
+        sp += __popc(m_int);
+
+        // leaf entries that satisfy the predicate
+        if (m_leaf != 0)
+        {
+          if (PASS == PASS_STASH || PASS == PASS_WRITE)
+          {
+            if (hit && is_leaf)
+            {
+              const uint32_t at = count + __popc(m_leaf & lt_mask);
+              if (buffered)
+              {
+                if (at < HIT_BUF)
+                  hitbuf[at] = link;
+              }
+              else if (PASS == PASS_WRITE && at < expect)
+              {
+                p.ids[out_base + at] = link;
+              }
+            }
+          }
+          count += __popc(m_leaf);
+        }
+        __syncwarp();
+      }
+
+      // ---- end of query ------------------------------------------------------------
+      if (PASS == PASS_COUNT || PASS == PASS_COUNT_STATS)
+      {
+        if (lane == 0)
+          p.counts[qi] = count;
+      }
+      else if (PASS == PASS_STASH)
+      {
+        uint32_t where = NO_STASH;
+        if (count == 0)
+        {
+          where = 0;
+        }
+        else if (count <= HIT_BUF)
+        {
+          if (slab_left < count)
+          {
+            unsigned long long got = 0;
+            if (lane == 0)
+              got = atomicAdd(p.stash_cursor, (unsigned long long)STASH_SLAB);
+            got = __shfl_sync(0xFFFFFFFFu, got, 0);
+            if (got + STASH_SLAB <= p.stash_capacity)
+            {
+              slab_pos = got;
+              slab_left = STASH_SLAB;
+            }
+            else
+            {
+              slab_left = 0; // pool exhausted: this and later queries are deferred
+            }
+          }
+          if (slab_left >= count)
+          {
+            uint32_t v = ((uint32_t)lane < count) ? hitbuf[lane] : RT_INVALID_ID;
+            if (p.sorted)
+              v = warp_sort32(v, lane);
+            if ((uint32_t)lane < count)
+              p.stash[slab_pos + lane] = v;
+            where = (uint32_t)slab_pos;
+            slab_pos += count;
+            slab_left -= count;
+          }
+        }
+        if (lane == 0)
+        {
+          p.counts[qi] = count;
+          p.stash_pos[qi] = where;
+          if (where == NO_STASH)
+            p.deferred_list[atomicAdd(p.deferred_count, 1u)] = (uint32_t)qi;
+        }
+      }
+      else // PASS_WRITE
+      {
+        if (buffered)
+        {
+          uint32_t v = ((uint32_t)lane < count) ? hitbuf[lane] : RT_INVALID_ID;
+          v = warp_sort32(v, lane);
+          if ((uint32_t)lane < count && (uint32_t)lane < expect)
+            p.ids[out_base + lane] = v;
+        }
+        else if (p.sorted && expect > 1 && lane == 0)
+        {
+          p.big_list[atomicAdd(p.big_count, 1u)] = (uint32_t)qi;
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  if (PASS == PASS_COUNT_STATS && lane == 0)
+  {
+    atomicAdd(p.visit_stats + 0, visits_int);
+    atomicAdd(p.visit_stats + 1, visits_leaf);
+  }
+}
+
+template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS>
+cudaError_t launch_box_pass(const BoxLaunch& p)
+{
+  auto kernel = box_traverse_kernel<S, D, W, BOXKEY, CONTAINS, PASS>;
+  const size_t smem = (size_t)(TRAVERSE_THREADS / 32) * (32u * p.tree.num_levels + HIT_BUF) * sizeof(uint32_t);
+  cudaError_t err = cudaSuccess;
+  if (smem > 48 * 1024)
+  {
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess)
+      return err;
+  }
+  int grid = p.grid;
+  if (grid <= 0)
+  {
+    int device = 0, sms = 0, per_sm = 0;
+    if ((err = cudaGetDevice(&device)) != cudaSuccess)
+      return err;
+    if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+      return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRAVERSE_THREADS, smem))
+        != cudaSuccess)
+      return err;
+    if (per_sm < 1)
+      per_sm = 1;
+    grid = sms * per_sm; // persistent: every resident warp pulls query chunks until none is left
+  }
+  const unsigned long long chunks = (p.n + QUERY_CHUNK - 1) / QUERY_CHUNK;
+  const unsigned long long needed = (chunks + TRAVERSE_THREADS / 32 - 1) / (TRAVERSE_THREADS / 32);
+  if ((unsigned long long)grid > needed)
+    grid = (int)(needed > 0 ? needed : 1);
+  kernel<<<grid, TRAVERSE_THREADS, smem, p.stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <typename S, int D, int W, bool BOXKEY, bool CONTAINS>
+cudaError_t launch_box(const BoxLaunch& p)
+{
+  switch (p.pass)
+  {
+  case PASS_COUNT: return launch_box_pass<S, D, W, BOXKEY, CONTAINS, PASS_COUNT>(p);
+  case PASS_COUNT_STATS: return launch_box_pass<S, D, W, BOXKEY, CONTAINS, PASS_COUNT_STATS>(p);
+  case PASS_STASH: return launch_box_pass<S, D, W, BOXKEY, CONTAINS, PASS_STASH>(p);
+  case PASS_WRITE: return launch_box_pass<S, D, W, BOXKEY, CONTAINS, PASS_WRITE>(p);
+  default: return cudaErrorInvalidValue;
+  }
+}
+
+// the instantiation list of one scalar type: (dim, width) pairs, point and box keys
+#define RTB_BOX_CASE(S, D, W)                                                                 \
+  if (dim == D && width == W)                                                                 \
+  {                                                                                           \
+    if (key_kind == RT_KEY_POINT)                                                             \
+      return &launch_box<S, D, W, false, false>;                                              \
+    if (mode == RT_CONTAINS)                                                                  \
+      return &launch_box<S, D, W, true, true>;                                                \
+    return &launch_box<S, D, W, true, false>;                                                 \
+  }
+
+} // namespace rtb

@@ -1,0 +1,258 @@
+// rt_traverse_ray.cuh -- warp-cooperative ray queries on the same block layout (sm_100a).
+//
+// The reference has no ray code; a ray query is RTree::search() (reference
+// include/RTree/rtree.hpp:984-1019) driven by a slab-test filter, which the API allows
+// because functors are held by reference (rtree.hpp:1145) and may be stateful:
+//   all-hits : filter = slab hit; functor collects the key ids whose AABB is hit
+//   closest  : filter = slab hit && t <= t_best (non-strict: ties survive);
+//              functor keeps (t, id) minimal, ties to the smaller id
+//   any-hit  : functor returns true on the first hit = abort (rtree.hpp:994-997)
+//
+// Slab test -- identical operation for operation to oracle/slab.h so that host and
+// device round the same way (only sub, mul, compare-select: nothing an FMA could fuse):
+//   a = (lo - o) * inv ; c = (hi - o) * inv ; near/far by (c < a)
+//   t0 = (near > t0) ? near : t0 ; t1 = (far < t1) ? far : t1 ; hit iff t0 <= t1
+//
+// Lane mapping, stack discipline and hit compaction are those of rt_traverse_box.cuh.
+// The closest-hit result is independent of traversal order: a key with the final
+// (t, id) can never be pruned because every ancestor bound has t_entry <= t.
+#pragma once
+
+#include "rt_common.cuh"
+#include "rt_traverse_box.cuh"
+
+namespace rtb
+{
+
+enum : uint32_t
+{
+  RAY_COUNT = 0,
+  RAY_COUNT_STATS = 1,
+  RAY_WRITE = 2,
+  RAY_CLOSEST = 3,
+  RAY_ANY = 4
+};
+
+template <int W, bool BOXKEY, uint32_t RMODE>
+__global__ void __launch_bounds__(TRAVERSE_THREADS)
+ray_traverse_kernel(const RayLaunch p)
+{
+  constexpr int G = 32 / W;
+  constexpr int D = 3;
+  extern __shared__ uint32_t smem[];
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int slot = lane % W;
+  const int grp = lane / W;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  const uint32_t stack_cap = 32u * p.tree.num_levels;
+  uint32_t* stack = smem + warp * (stack_cap + HIT_BUF);
+  uint32_t* hitbuf = stack + stack_cap;
+
+  const unsigned char* __restrict__ int_base = p.tree.blocks;
+  const unsigned char* __restrict__ leaf_base = p.tree.blocks + p.tree.leaf_offset;
+  const uint32_t leaf_begin = p.tree.leaf_begin;
+  const uint32_t int_stride = p.tree.internal_stride;
+  const uint32_t leaf_stride = p.tree.leaf_stride;
+  constexpr uint32_t LINK_OFF_INTERNAL = 2u * D * W * sizeof(float);
+  constexpr uint32_t LINK_OFF_LEAF = (BOXKEY ? 2u : 1u) * D * W * sizeof(float);
+
+  unsigned long long visits_int = 0, visits_leaf = 0, rays_hit = 0;
+
+  for (;;)
+  {
+    unsigned long long first = 0;
+    if (lane == 0)
+      first = atomicAdd(p.work_counter, (unsigned long long)QUERY_CHUNK);
+    first = __shfl_sync(0xFFFFFFFFu, first, 0);
+    if (first >= p.n)
+      break;
+    const unsigned long long last = min(first + (unsigned long long)QUERY_CHUNK, (unsigned long long)p.n);
+
+    for (unsigned long long i = first; i < last; ++i)
+    {
+      const unsigned long long qi = p.order ? (unsigned long long)p.order[i] : i;
+      float org[D], inv[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+      {
+        org[d] = __ldg(p.rays + qi * 7 + d);
+        inv[d] = __ldg(p.rays + qi * 7 + 3 + d);
+      }
+      const float tmax = __ldg(p.rays + qi * 7 + 6);
+
+      unsigned long long out_base = 0;
+      uint32_t expect = 0;
+      bool buffered = false;
+      if (RMODE == RAY_WRITE)
+      {
+        out_base = p.offsets[qi];
+        expect = (uint32_t)min(p.offsets[qi + 1] - out_base, (unsigned long long)0xFFFFFFFFu);
+        buffered = p.sorted && expect <= HIT_BUF;
+      }
+
+      float t_best = tmax;
+      uint32_t id_best = RT_INVALID_ID;
+      bool found = false;
+      uint32_t count = 0;
+      uint32_t sp = 1;
+      if (lane == 0)
+        stack[0] = 0;
+      __syncwarp();
+
+      while (sp > 0)
+      {
+        const uint32_t take = min(sp, (uint32_t)G);
+        sp -= take;
+        const bool active = (uint32_t)grp < take;
+        uint32_t node = RT_INVALID_ID;
+        if (active)
+          node = stack[sp + grp];
+        __syncwarp();
+
+        const bool is_leaf = node >= leaf_begin;
+        const unsigned char* blk = is_leaf
+                                       ? leaf_base + (unsigned long long)(node - leaf_begin) * leaf_stride
+                                       : int_base + (unsigned long long)node * int_stride;
+        const bool one_corner = !BOXKEY && is_leaf;
+
+        uint32_t link = RT_INVALID_ID;
+        bool hit = false;
+        float t0 = 0.0f;
+        if (active)
+        {
+          const float* row = reinterpret_cast<const float*>(blk) + slot;
+          link = __ldg(reinterpret_cast<const uint32_t*>(blk + (is_leaf ? LINK_OFF_LEAF : LINK_OFF_INTERNAL)) + slot);
+          float lo[D], hi[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d)
+            lo[d] = __ldg(row + d * W);
+#pragma unroll
+          for (int d = 0; d < D; ++d)
+            hi[d] = one_corner ? lo[d] : __ldg(row + (D + d) * W);
+          float t1 = tmax;
+#pragma unroll
+          for (int d = 0; d < D; ++d)
+          {
+            const float a = __fmul_rn(__fsub_rn(lo[d], org[d]), inv[d]);
+            const float c = __fmul_rn(__fsub_rn(hi[d], org[d]), inv[d]);
+            const float tn = (c < a) ? c : a;
+            const float tf = (c < a) ? a : c;
+            t0 = (tn > t0) ? tn : t0;
+            t1 = (tf < t1) ? tf : t1;
+          }
+          hit = (link != RT_INVALID_ID) && (t0 <= t1);
+          if (RMODE == RAY_CLOSEST)
+            hit = hit && (is_leaf || t0 <= t_best);
+        }
+
+        const uint32_t m_all = __ballot_sync(0xFFFFFFFFu, hit);
+        const uint32_t m_leaf = __ballot_sync(0xFFFFFFFFu, hit && is_leaf);
+        const uint32_t m_int = m_all & ~m_leaf;
+
+        if (RMODE == RAY_COUNT_STATS)
+        {
+          const uint32_t leaf_nodes = __popc(__ballot_sync(0xFFFFFFFFu, active && is_leaf && slot == 0));
+          visits_leaf += leaf_nodes;
+          visits_int += take - leaf_nodes;
+        }
+
+        if (hit && !is_leaf)
+          stack[sp + __popc(m_int & lt_mask)] = link;
+        sp += __popc(m_int);
+
+        if (m_leaf != 0)
+        {
+          if (RMODE == RAY_CLOSEST)
+          {
+            // t0 >= +0 and never NaN, so its bit pattern orders like the value
+            const bool cand = hit && is_leaf;
+            const uint32_t t_bits = __reduce_min_sync(0xFFFFFFFFu, cand ? __float_as_uint(t0) : 0xFFFFFFFFu);
+            const uint32_t id_min = __reduce_min_sync(
+                0xFFFFFFFFu, (cand && __float_as_uint(t0) == t_bits) ? link : RT_INVALID_ID);
+            const float t = __uint_as_float(t_bits);
+            if (!found || t < t_best || (t == t_best && id_min < id_best))
+            {
+              found = true;
+              t_best = t;
+              id_best = id_min;
+            }
+          }
+          else if (RMODE == RAY_ANY)
+          {
+            found = true;
+            sp = 0; // abort the whole search
+          }
+          else
+          {
+            if (RMODE == RAY_WRITE && hit && is_leaf)
+            {
+              const uint32_t at = count + __popc(m_leaf & lt_mask);
+              if (buffered)
+              {
+                if (at < HIT_BUF)
+                  hitbuf[at] = link;
+              }
+              else if (at < expect)
+              {
+                p.ids[out_base + at] = link;
+              }
+            }
+            count += __popc(m_leaf);
+          }
+        }
+        __syncwarp();
+      }
+
+      if (RMODE == RAY_COUNT || RMODE == RAY_COUNT_STATS)
+      {
+        if (lane == 0)
+          p.counts[qi] = count;
+      }
+      else if (RMODE == RAY_WRITE)
+      {
+        if (buffered)
+        {
+          uint32_t v = ((uint32_t)lane < count) ? hitbuf[lane] : RT_INVALID_ID;
+          v = warp_sort32(v, lane);
+          if ((uint32_t)lane < count && (uint32_t)lane < expect)
+            p.ids[out_base + lane] = v;
+        }
+        else if (p.sorted && expect > 1 && lane == 0)
+        {
+          p.big_list[atomicAdd(p.big_count, 1u)] = (uint32_t)qi;
+        }
+      }
+      else if (RMODE == RAY_CLOSEST)
+      {
+        if (lane == 0)
+        {
+          p.t_out[qi] = found ? t_best : __uint_as_float(0x7F800000u);
+          p.id_out[qi] = id_best;
+          rays_hit += found ? 1 : 0;
+        }
+      }
+      else // RAY_ANY
+      {
+        if (lane == 0)
+        {
+          p.any_out[qi] = found ? 1 : 0;
+          rays_hit += found ? 1 : 0;
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  if (RMODE == RAY_COUNT_STATS && lane == 0)
+  {
+    atomicAdd(p.visit_stats + 0, visits_int);
+    atomicAdd(p.visit_stats + 1, visits_leaf);
+  }
+  if ((RMODE == RAY_CLOSEST || RMODE == RAY_ANY) && lane == 0 && rays_hit != 0)
+    atomicAdd(p.visit_stats + 2, rays_hit);
+}
+
+} // namespace rtb

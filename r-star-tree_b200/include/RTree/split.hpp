@@ -173,110 +173,114 @@ struct QuadraticSplit
     constexpr int M = static_cast<int>(NodeType::MAX_ENTRIES);
     constexpr int m = static_cast<int>(NodeType::MIN_ENTRIES);
     constexpr int COUNT = M + 1;
+    constexpr int EXTRA = M; // index of the overflowing entry in the scratch set
 
     detail::overflow_set<NodeType> set(node, std::move(extra));
     auto& entries = set.entries;
-
-    // PickSeeds: the pair that wastes most area when put together; ties go to the
-    // pair with the smaller intersection
-    int seed1 = 0, seed2 = 1;
+    auto waste_of = [&](int i, int j)
     {
-      scalar worst = std::numeric_limits<scalar>::lowest();
-      scalar worst_inter = 0;
-      bool have = false;
-      for (int i = 0; i < COUNT - 1; ++i)
+      const geometry_type gi(entries[i].first), gj(entries[j].first);
+      return helper::enlarged_area(gi, gj) - helper::area(gi) - helper::area(gj);
+    };
+    auto overlap_of = [&](int i, int j)
+    {
+      const geometry_type gi(entries[i].first), gj(entries[j].first);
+      return helper::intersection_area(gi, gj);
+    };
+
+    // PickSeeds: the pair that wastes most area when grouped; equal waste goes to the pair
+    // with the smaller intersection.  Pairs among the old entries are examined first, then
+    // the overflowing entry against each of them (the order decides exact ties).
+    int seed_a = 0, seed_b = 0;
+    scalar worst = std::numeric_limits<scalar>::lowest();
+    auto consider = [&](int i, int j)
+    {
+      const scalar waste = waste_of(i, j);
+      if (waste > worst || (waste == worst && overlap_of(i, j) < overlap_of(seed_a, seed_b)))
       {
-        const geometry_type gi(entries[i].first);
-        const scalar ai = helper::area(gi);
-        for (int j = i + 1; j < COUNT; ++j)
-        {
-          const geometry_type gj(entries[j].first);
-          const scalar waste = helper::enlarged_area(gi, gj) - ai - helper::area(gj);
-          if (!have || waste > worst)
-          {
-            have = true;
-            worst = waste;
-            worst_inter = helper::intersection_area(gi, gj);
-            seed1 = i;
-            seed2 = j;
-          }
-          else if (waste == worst)
-          {
-            const scalar inter = helper::intersection_area(gi, gj);
-            if (inter < worst_inter)
-            {
-              worst_inter = inter;
-              seed1 = i;
-              seed2 = j;
-            }
-          }
-        }
+        worst = waste;
+        seed_a = i;
+        seed_b = j;
       }
+    };
+    for (int i = 0; i < M - 1; ++i)
+      for (int j = i + 1; j < M; ++j)
+        consider(i, j);
+    for (int j = 0; j < M; ++j)
+      consider(EXTRA, j);
+
+    // `left` lists the entries still in (or heading for) the old node, in slot order; its
+    // first `settled` ones are assigned.  `right` is the new node.  Removing from `left`
+    // moves its last element into the hole, so the final slot order is well defined.
+    std::array<int, COUNT> left, right;
+    int n_left = M, n_right = 0, settled = 1;
+    for (int i = 0; i < M; ++i)
+      left[i] = i;
+    auto take_from_left = [&](int pos)
+    {
+      right[n_right++] = left[pos];
+      left[pos] = left[n_left - 1];
+      --n_left;
+    };
+    if (seed_a == EXTRA)
+    {
+      right[n_right++] = EXTRA;
+      std::swap(left[0], left[seed_b]);
     }
-
-    std::array<int, COUNT> group; // -1 unassigned, 0 -> node, 1 -> pair
-    group.fill(-1);
-    group[seed1] = 0;
-    group[seed2] = 1;
-    geometry_type bound0(entries[seed1].first);
-    geometry_type bound1(entries[seed2].first);
-    int count0 = 1, count1 = 1, left = COUNT - 2;
-
-    while (left > 0)
+    else
     {
-      // a group that needs every remaining entry to reach m takes them all
-      if (count0 + left == m)
+      take_from_left(seed_b); // seed_a < seed_b, so slot seed_a is untouched
+      std::swap(left[0], left[seed_a]);
+      left[n_left++] = EXTRA;
+    }
+    geometry_type bound_left(entries[left[0]].first);
+    geometry_type bound_right(entries[right[0]].first);
+
+    while (settled + n_right < COUNT)
+    {
+      const int open = COUNT - (settled + n_right);
+      if (settled + open == m)
+        break; // everything still open stays left
+      if (n_right + open == m)
       {
-        for (int i = 0; i < COUNT; ++i)
-          if (group[i] == -1)
-            group[i] = 0;
+        for (int k = 0; k < open; ++k)
+          take_from_left(n_left - 1);
         break;
       }
-      if (count1 + left == m)
-      {
-        for (int i = 0; i < COUNT; ++i)
-          if (group[i] == -1)
-            group[i] = 1;
-        break;
-      }
-      // PickNext: the entry with the strongest preference for one group
-      int pick = -1, pick_to = 0;
+      // PickNext: the open entry with the strongest preference for one side
+      int pick = settled;
+      bool to_left = true;
       scalar strongest = std::numeric_limits<scalar>::lowest();
-      for (int i = 0; i < COUNT; ++i)
+      for (int pos = settled; pos < n_left; ++pos)
       {
-        if (group[i] != -1)
-          continue;
-        const scalar d0 = helper::enlarged_area(bound0, entries[i].first) - helper::area(bound0);
-        const scalar d1 = helper::enlarged_area(bound1, entries[i].first) - helper::area(bound1);
-        const scalar diff = d0 < d1 ? d1 - d0 : d0 - d1;
-        if (pick == -1 || diff > strongest)
+        auto const& g = entries[left[pos]].first;
+        const scalar d_left = helper::enlarged_area(bound_left, g) - helper::area(bound_left);
+        const scalar d_right = helper::enlarged_area(bound_right, g) - helper::area(bound_right);
+        const scalar preference = d_left < d_right ? d_right - d_left : d_left - d_right;
+        if (preference > strongest)
         {
-          pick = i;
-          strongest = diff;
-          pick_to = d0 < d1 ? 0 : 1;
+          strongest = preference;
+          pick = pos;
+          to_left = d_left < d_right;
         }
       }
-      group[pick] = pick_to;
-      if (pick_to == 0)
+      if (to_left)
       {
-        helper::enlarge_to(bound0, entries[pick].first);
-        ++count0;
+        helper::enlarge_to(bound_left, entries[left[pick]].first);
+        std::swap(left[settled], left[pick]);
+        ++settled;
       }
       else
       {
-        helper::enlarge_to(bound1, entries[pick].first);
-        ++count1;
+        helper::enlarge_to(bound_right, entries[left[pick]].first);
+        take_from_left(pick);
       }
-      --left;
     }
 
-    for (int i = 0; i < COUNT; ++i)
-    {
-      if (group[i] == 1)
-        pair->insert(std::move(entries[i]));
-      else
-        node->insert(std::move(entries[i]));
-    }
+    for (int i = 0; i < n_left; ++i)
+      node->insert(std::move(entries[left[i]]));
+    for (int i = 0; i < n_right; ++i)
+      pair->insert(std::move(entries[right[i]]));
     return pair;
   }
 };

@@ -1,0 +1,94 @@
+"""CPU tests of the C-ABI boundary: the CUDA library loads without a GPU, exports every symbol
+include/rtree_b200.h declares, its structs have the documented layout, and the product fails
+LOUDLY (no fallback) when no device is present.  No compute calls are made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+
+def declared_symbols(header_path):
+    text = open(header_path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rt_[a-z_]+)\s*\(", text)))
+
+
+def test_library_is_built(rtb):
+    assert rtb.capi.have_library(), "run __graft_entry__.build()"
+    assert rtb.host.have_library()
+
+
+def test_every_declared_symbol_is_exported(rtb):
+    names = declared_symbols(rtb.capi.HEADER_PATH)
+    assert {"rt_upload", "rt_query_boxes", "rt_query_rays", "rt_free"} <= set(names)
+    assert sorted(names) == sorted(rtb.capi.EXPORTS)
+    lib = C.CDLL(rtb.capi.LIB_PATH)
+    for name in names:
+        assert hasattr(lib, name), name
+
+
+def test_abi_version_and_struct_sizes(rtb):
+    capi = rtb.capi
+    assert capi.lib().rt_abi_version() == capi.RT_ABI_VERSION == 1
+    # x86-64 layouts of the structs in include/rtree_b200.h
+    assert C.sizeof(capi.RtTreeDesc) == 88
+    assert C.sizeof(capi.RtHits) == 40
+    assert C.sizeof(capi.RtRayResult) == 88
+    assert C.sizeof(capi.RtStats) == 56
+
+
+def test_header_compiles_as_plain_c(rtb, tmp_path):
+    src = tmp_path / "abi.c"
+    src.write_text('#include <rtree_b200.h>\n#include <stddef.h>\n'
+                   'int sizes[4] = { sizeof(rt_tree_desc), sizeof(rt_hits), sizeof(rt_ray_result), sizeof(rt_stats) };\n'
+                   'int main(void) { return sizes[0] == 88 && sizes[1] == 40 && sizes[2] == 88 && sizes[3] == 56 ? 0 : 1; }\n')
+    exe = tmp_path / "abi"
+    inc = os.path.dirname(rtb.capi.HEADER_PATH)
+    assert os.system("/usr/bin/gcc -std=c99 -Wall -Werror -I%s -o %s %s" % (inc, exe, src)) == 0
+    assert os.system(str(exe)) == 0
+
+
+def _no_gpu(rtb):
+    return rtb.capi.lib().rt_device_count() <= 0
+
+
+def test_fails_loudly_without_a_device(rtb):
+    if not _no_gpu(rtb):
+        pytest.skip("a CUDA device is present")
+    image = rtb.RTree(4).insert(np.random.default_rng(0).random((100, 3)).astype(np.float32)).flatten_device()
+    with pytest.raises(rtb.RtError) as err:
+        image.upload(0)
+    assert err.value.code == rtb.capi.RT_E_CUDA
+    assert "CUDA" in str(err.value) or "device" in str(err.value)
+
+
+def test_argument_validation(rtb):
+    capi = rtb.capi
+    lib = capi.lib()
+    handle = C.c_void_p()
+    assert lib.rt_upload(None, 0, C.byref(handle)) == capi.RT_E_INVALID
+    image = rtb.RTree(4).insert(np.random.default_rng(0).random((100, 3)).astype(np.float32)).flatten_device()
+    bad = capi.RtTreeDesc.from_buffer_copy(image.desc)
+    bad.abi_version = 99
+    assert lib.rt_upload(C.byref(bad), 0, C.byref(handle)) == capi.RT_E_INVALID
+    bad = capi.RtTreeDesc.from_buffer_copy(image.desc)
+    bad.width = 12
+    assert lib.rt_upload(C.byref(bad), 0, C.byref(handle)) == capi.RT_E_UNSUPPORTED
+    bad = capi.RtTreeDesc.from_buffer_copy(image.desc)
+    bad.blocks_bytes = 16
+    assert lib.rt_upload(C.byref(bad), 0, C.byref(handle)) == capi.RT_E_INVALID
+    assert b"blocks_bytes" in lib.rt_last_error()
+    out = capi.RtHits()
+    assert lib.rt_query_boxes(None, None, 0, 0, 0, C.byref(out)) == capi.RT_E_INVALID
+    lib.rt_free(None)  # documented no-op
+
+
+def test_missing_library_is_an_error_not_a_fallback(rtb, monkeypatch):
+    capi = rtb.capi
+    monkeypatch.setattr(capi, "_lib", None)
+    monkeypatch.setattr(capi, "LIB_PATH", capi.LIB_PATH + ".absent")
+    with pytest.raises(rtb.RtError) as err:
+        capi.lib()
+    assert "no CPU fallback" in str(err.value)

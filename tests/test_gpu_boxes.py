@@ -1,0 +1,247 @@
+"""GPU parity tests for rt_query_boxes -- every call goes through the C ABI
+(include/rtree_b200.h) into the sm_100a kernels and is compared bit-exactly with the oracle:
+golden vectors made by the reference, the reference run live (oracle/_ref), the C restatement
+and brute force.  Integer / index work: the bar is exact equality."""
+import os
+
+import numpy as np
+import pytest
+
+import oracles as O
+from helpers import csr_equal
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+BOX_FIXTURES = ["flatten_test_1d_i32", "sample_1d_f64", "config1_2d_f64", "config2_cut_3d_f32",
+                "config4_cut_8d_f32", "teapot_boxes_intersects", "teapot_boxes_contains", "lattice_2d_i32"]
+
+
+def upload_flat(rtb, kind, flat):
+    image = rtb.DeviceImage.from_flat(kind, flat.leaf_level, flat.nodes, flat.bounds, flat.children, flat.data)
+    return image.upload(0)
+
+
+def sort_segments(off, ids):
+    out = ids.copy()
+    for i in range(len(off) - 1):
+        out[off[i]:off[i + 1]].sort()
+    return out
+
+
+@pytest.mark.parametrize("name", BOX_FIXTURES)
+def test_golden_vectors_all_pipelines(rtb, name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    flat = O.Flat.load(z)
+    kind, mode, q = int(z["kind"]), int(z["mode"]), z["queries"]
+    want = (z["offsets"], z["ids"])
+    with upload_flat(rtb, kind, flat) as tree:
+        assert csr_equal(tree.query_boxes(q, mode), want)                                   # stash pipeline
+        assert tree.stats()["kernel_launches"] > 0
+        assert csr_equal(tree.query_boxes(q, mode, rtb.RT_NO_REORDER), want)
+        off, ids = tree.query_boxes(q, mode, rtb.RT_COLLECT_VISITS)                         # two-pass pipeline
+        assert csr_equal((off, ids), want)
+        s = tree.stats()
+        _, _, visits = O.oracle_query_boxes(flat, q, mode, want_visits=True)
+        assert (s["visits_internal"], s["visits_leaf"]) == (int(visits[0]), int(visits[1]))
+        assert s["algorithmic_bytes"] > 0
+        off, ids = tree.query_boxes(q, mode, rtb.RT_UNSORTED)
+        assert np.array_equal(off, want[0]) and np.array_equal(sort_segments(off, ids), want[1])
+        off, ids = tree.query_boxes(q, mode, rtb.RT_COUNT_ONLY)
+        assert np.array_equal(off, want[0]) and ids.size == 0
+
+
+@pytest.mark.parametrize("kind", sorted(O.KINDS))
+def test_product_tree_vs_reference_search(rtb, kind):
+    """tree built by the product's host library, queried on the GPU, against the reference's own
+    RTree::search() on the reference's own tree (hit sets are topology independent)"""
+    scalar, dim, is_box, _ = O.KINDS[kind]
+    rng = np.random.default_rng(200 + kind)
+    n, nq = 20000, 6000
+    if scalar == O.I32:
+        keys = rng.integers(0, 300, (n, dim)).astype(np.int32)
+        lo = rng.integers(-5, 300, (nq, dim))
+        q = np.stack([lo, lo + rng.integers(0, 9, (nq, dim))], axis=1).astype(np.int32)
+    else:
+        dt = O.SCALAR_DTYPES[scalar]
+        c = rng.random((n, dim))
+        if is_box:
+            h = rng.uniform(0, 0.01, (n, dim))
+            keys = np.stack([c - h, c + h], axis=1).astype(dt)
+        else:
+            keys = c.astype(dt)
+        qc = rng.random((nq, dim))
+        qh = 0.5 * (10.0 / n) ** (1.0 / dim) * rng.uniform(0.3, 3.0, (nq, 1))
+        q = np.stack([qc - qh, qc + qh], axis=1).astype(dt)
+    modes = [rtb.RT_INTERSECTS, rtb.RT_CONTAINS] if is_box else [rtb.RT_POINT_IN_BOX]
+    ref = O.RefTree(kind).insert(keys)
+    with rtb.RTree(kind).insert(keys).flatten_device().upload(0) as tree:
+        for mode in modes:
+            want = ref.search_boxes(q, mode)
+            assert want[1].size > 0
+            assert csr_equal(tree.query_boxes(q, mode), want)
+            assert csr_equal(tree.query_boxes(q, mode, rtb.RT_COLLECT_VISITS), want)
+
+
+def test_point_tree_accepts_every_mode_box_tree_rejects_point_mode(rtb):
+    pts = rtb.workloads.uniform_points(5000, seed=1)
+    q = rtb.workloads.cube_queries(500, 5000, seed=2)
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+        a = tree.query_boxes(q, rtb.RT_POINT_IN_BOX)
+        assert csr_equal(a, tree.query_boxes(q, rtb.RT_INTERSECTS))
+        assert csr_equal(a, tree.query_boxes(q, rtb.RT_CONTAINS))
+    boxes = np.stack([pts, pts + 0.01], axis=1)
+    with rtb.RTree(5).insert(boxes).flatten_device().upload(0) as tree:
+        with pytest.raises(rtb.RtError) as err:
+            tree.query_boxes(q, rtb.RT_POINT_IN_BOX)
+        assert err.value.code == rtb.capi.RT_E_INVALID
+
+
+def test_edge_cases_nan_inverted_everything(rtb):
+    rng = np.random.default_rng(9)
+    pts = rng.random((3000, 3)).astype(np.float32)
+    q = np.zeros((7, 2, 3), np.float32)
+    q[0] = [[0.2, 0.2, 0.2], [0.4, np.nan, 0.4]]
+    q[1] = [[np.nan, 0.1, 0.1], [0.3, 0.3, 0.3]]
+    q[2] = [[0.6, 0.6, 0.6], [0.5, 0.5, 0.5]]
+    q[3] = [pts[17], pts[17]]
+    q[4] = [[-np.inf] * 3, [np.inf] * 3]
+    q[5] = [[np.nan] * 3, [np.nan] * 3]
+    q[6] = [[2, 2, 2], [3, 3, 3]]
+    want = O.RefTree(4).insert(pts).search_boxes(q)
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+        assert csr_equal(tree.query_boxes(q), want)
+        assert csr_equal(tree.query_boxes(q, flags=rtb.RT_COLLECT_VISITS), want)
+        # a large batch takes the reorder path even with NaN / inf centres in it
+        big = np.concatenate([q, rtb.workloads.cube_queries(9000, 3000, seed=5)])
+        want_big = O.RefTree(4).insert(pts).search_boxes(big)
+        assert csr_equal(tree.query_boxes(big), want_big)
+
+
+def test_empty_tree_root_leaf_tree_and_empty_batch(rtb):
+    q = rtb.workloads.cube_queries(10, 10, seed=2)
+    with rtb.RTree(4).flatten_device().upload(0) as tree:                   # appendix B4
+        off, ids = tree.query_boxes(q)
+        assert off.tolist() == [0] * 11 and ids.size == 0
+    pts = np.array([[0.1, 0.1, 0.1], [0.5, 0.5, 0.5], [0.9, 0.9, 0.9]], np.float32)
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:      # root is a leaf
+        off, ids = tree.query_boxes(np.array([[[0.4, 0.4, 0.4], [1, 1, 1]], [[0, 0, 0], [0.2, 0.2, 0.2]]], np.float32))
+        assert off.tolist() == [0, 2, 3] and ids.tolist() == [1, 2, 0]
+        off, ids = tree.query_boxes(np.zeros((0, 2, 3), np.float32))       # n == 0
+        assert off.tolist() == [0] and ids.size == 0
+        off, ids = tree.query_boxes(np.array([[[0, 0, 0], [1, 1, 1]]], np.float32))
+        assert ids.tolist() == [0, 1, 2]
+
+
+def test_long_hit_lists_take_the_deferred_and_sort_paths(rtb):
+    """lists of 33..8192 ids are sorted in shared memory, longer ones in global memory; the
+    whole-tree query returns every id exactly once"""
+    n = 40000
+    pts = rtb.workloads.uniform_points(n, seed=3)
+    ref = O.RefTree(4).insert(pts)
+    q = np.concatenate([rtb.workloads.cube_queries(300, n, seed=4, hits_per_query=200.0),
+                        rtb.workloads.cube_queries(40, n, seed=5, hits_per_query=9000.0),
+                        np.array([[[-1, -1, -1], [2, 2, 2]]], np.float32),
+                        rtb.workloads.cube_queries(300, n, seed=6, hits_per_query=5.0)])
+    want = ref.search_boxes(q)
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+        got = tree.query_boxes(q)
+        assert csr_equal(got, want)
+        s = tree.stats()
+        assert s["deferred_queries"] >= 341
+        whole = got[1][got[0][340]:got[0][341]]
+        assert np.array_equal(whole, np.arange(n))
+        assert csr_equal(tree.query_boxes(q, flags=rtb.RT_COLLECT_VISITS), want)
+
+
+def test_stash_exhaustion_falls_back_to_the_second_traversal(rtb, monkeypatch):
+    n = 30000
+    pts = rtb.workloads.uniform_points(n, seed=7)
+    q = rtb.workloads.cube_queries(20000, n, seed=8)
+    want = O.RefTree(4).insert(pts).search_boxes(q)
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+        monkeypatch.setenv("RTB_STASH_LIMIT_IDS", "4096")
+        got = tree.query_boxes(q)
+        assert tree.stats()["deferred_queries"] > 1000
+        assert csr_equal(got, want)
+        monkeypatch.setenv("RTB_STASH_LIMIT_IDS", "0")
+        got = tree.query_boxes(q)
+        assert tree.stats()["deferred_queries"] >= int((np.diff(want[0].astype(np.int64)) > 0).sum())
+        assert csr_equal(got, want)
+        monkeypatch.delenv("RTB_STASH_LIMIT_IDS")
+        assert csr_equal(tree.query_boxes(q), want)
+        assert tree.stats()["deferred_queries"] == 0
+
+
+def test_device_resident_queries_and_results(rtb):
+    """RT_QUERIES_ON_DEVICE | RT_RESULT_ON_DEVICE with torch owning the memory and the stream"""
+    import ctypes as C
+    import torch
+    n = 20000
+    pts = rtb.workloads.uniform_points(n, seed=1)
+    q = rtb.workloads.cube_queries(30000, n, seed=2)
+    want = O.RefTree(4).insert(pts).search_boxes(q)
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+        stream = torch.cuda.Stream()
+        tree.set_stream(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            dq = torch.from_numpy(q).cuda(non_blocking=False)
+            stream.synchronize()
+            out = tree.query_boxes_raw(dq.data_ptr(), len(q), rtb.RT_POINT_IN_BOX,
+                                       rtb.RT_QUERIES_ON_DEVICE | rtb.RT_RESULT_ON_DEVICE)
+            assert out.memory == rtb.capi.RT_MEM_DEVICE and out.total == len(want[1])
+            # wrap the engine-owned device buffers without copying (__cuda_array_interface__)
+            off = torch.as_tensor(rtb.capi.DeviceBuffer(out.offsets, (len(q) + 1) * 8), device="cuda").view(torch.int64)
+            ids = torch.as_tensor(rtb.capi.DeviceBuffer(out.ids, out.total * 4), device="cuda").view(torch.int32)
+        assert np.array_equal(off.cpu().numpy().astype(np.uint64), want[0])
+        assert np.array_equal(ids.cpu().numpy().view(np.uint32), want[1])
+        tree.set_stream(0)
+
+
+def test_query_sharding_emulated_on_one_gpu(rtb):
+    """R contiguous shards answered separately concatenate to the 1-shard answer"""
+    n, nq = 50000, 40001
+    pts = rtb.workloads.uniform_points(n, seed=11)
+    q = rtb.workloads.cube_queries(nq, n, seed=12)
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+        full = tree.query_boxes(q)
+        for world in (2, 4, 8):
+            parts = []
+            for r in range(world):
+                b, e = rtb.sharding.shard_range(nq, world, r)
+                parts.append(tree.query_boxes(q[b:e]))
+            assert csr_equal(rtb.sharding.concat_csr(parts), full)
+        # a second handle (replica) on the same device gives the same answer
+        image = rtb.RTree(4).insert(pts).flatten_device()
+        with image.upload(0) as replica:
+            assert csr_equal(replica.query_boxes(q), full)
+            blocks = replica.device_blocks()
+            assert blocks.nbytes == image.desc.blocks_bytes
+
+
+def test_config2_scale_properties(rtb):
+    """BASELINE config 2 at a few million points / queries, checked through size-independent
+    properties: both pipelines agree, per-query lists are strictly ascending, every reported
+    point lies in its box, the count equals a brute-force count on a sample, and the result
+    is reproducible."""
+    n, nq = 2_000_000, 3_000_000
+    pts = rtb.workloads.uniform_points(n, seed=42)
+    q = rtb.workloads.cube_queries(nq, n, seed=43)
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+        off, ids = tree.query_boxes(q)
+        assert tree.stats()["deferred_queries"] == 0
+        off2, ids2 = tree.query_boxes(q, flags=rtb.RT_COLLECT_VISITS)
+        assert np.array_equal(off, off2) and np.array_equal(ids, ids2)
+        off3, ids3 = tree.query_boxes(q)
+        assert np.array_equal(off, off3) and np.array_equal(ids, ids3)
+    counts = np.diff(off.astype(np.int64))
+    assert 9.0 < counts.mean() < 11.0
+    owner = np.repeat(np.arange(nq), counts)
+    p = pts[ids]
+    assert np.all((p >= q[owner, 0]) & (p <= q[owner, 1]))                 # every hit is inside
+    same_owner = owner[1:] == owner[:-1]
+    assert np.all(ids[1:][same_owner] > ids[:-1][same_owner])             # ascending, no duplicates
+    sample = np.random.default_rng(0).integers(0, nq, 300)
+    for i in sample:                                                       # nothing is missing
+        inside = np.all((pts >= q[i, 0]) & (pts <= q[i, 1]), axis=1)
+        assert np.array_equal(np.nonzero(inside)[0].astype(np.uint32), ids[off[i]:off[i + 1]])

@@ -1,0 +1,163 @@
+"""CPU tests of the header-only host library (r-star-tree_b200/include/RTree.hpp) through the
+host bridge: the build side produces valid trees, flatten() is field-for-field the reference's
+format, search() returns the reference's hit sets, and flatten_device() lays the tree out as
+include/rtree_b200.h documents."""
+import numpy as np
+import pytest
+
+import oracles as O
+from helpers import decode_image, csr_equal
+
+needs_ref = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/libref_oracle.so not built")
+
+
+def make_keys(kind, n, seed):
+    scalar, dim, is_box, _ = O.KINDS[kind]
+    rng = np.random.default_rng(seed)
+    if scalar == O.I32:
+        return rng.integers(0, 200, (n, dim)).astype(np.int32)
+    if is_box:
+        c = rng.random((n, dim))
+        h = rng.uniform(0.0, 0.02, (n, dim))
+        return np.stack([c - h, c + h], axis=1).astype(O.SCALAR_DTYPES[scalar])
+    return rng.random((n, dim)).astype(O.SCALAR_DTYPES[scalar])
+
+
+def make_queries(kind, nq, n, seed):
+    scalar, dim, _, _ = O.KINDS[kind]
+    rng = np.random.default_rng(seed)
+    if scalar == O.I32:
+        lo = rng.integers(-5, 200, (nq, dim))
+        return np.stack([lo, lo + rng.integers(0, 40, (nq, dim))], axis=1).astype(np.int32)
+    c = rng.random((nq, dim))
+    h = 0.5 * (12.0 / n) ** (1.0 / dim) * rng.uniform(0.5, 2.0, (nq, 1))
+    return np.stack([c - h, c + h], axis=1).astype(O.SCALAR_DTYPES[scalar])
+
+
+@pytest.mark.parametrize("kind", sorted(O.KINDS))
+def test_insert_keeps_the_structural_invariants(rtb, kind):
+    """the invariants reference test/rtree.cpp:32-95 asserts after every insert"""
+    keys = make_keys(kind, 1200, kind)
+    tree = rtb.RTree(kind)
+    for start in range(0, 1200, 150):
+        tree.insert(keys[start:start + 150], first_id=start)
+        assert tree.check_invariants() == 0
+        assert tree.size() == start + 150
+    flat = tree.flatten()
+    assert sorted(flat["data"].tolist()) == list(range(1200))
+    assert flat["root"] == 0 and flat["nodes"][0, 2] == 0
+    sizes = flat["nodes"][1:, 1]
+    m = 8 if O.KINDS[kind][3] == 16 else 4
+    assert sizes.min() >= m and sizes.max() <= O.KINDS[kind][3]
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", sorted(O.KINDS))
+def test_flatten_is_bit_identical_to_the_reference(rtb, kind):
+    """same inputs -> the same tree and the same four flatten vectors as the reference"""
+    keys = make_keys(kind, 3000, 50 + kind)
+    mine = rtb.RTree(kind).insert(keys).flatten()
+    ref = O.RefTree(kind).insert(keys).flatten()
+    assert mine["leaf_level"] == ref.leaf_level
+    assert np.array_equal(mine["nodes"], ref.nodes)
+    assert np.array_equal(mine["children"], ref.children)
+    assert np.array_equal(mine["data"], ref.data)
+    assert np.array_equal(mine["children_bound"].view(np.uint8), ref.bounds.view(np.uint8))
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", [0, 2, 4, 5, 6, 8])
+def test_host_search_matches_reference_search(rtb, kind):
+    keys = make_keys(kind, 4000, 70 + kind)
+    q = make_queries(kind, 400, 4000, 80 + kind)
+    mode = O.MODE_INTERSECTS if O.KINDS[kind][2] else O.MODE_POINT_IN_BOX
+    mine = rtb.RTree(kind).insert(keys).search_boxes(q, mode)
+    ref = O.RefTree(kind).insert(keys).search_boxes(q, mode)
+    assert csr_equal(mine, ref) and ref[1].size > 0
+
+
+def test_erase_clear_rebalance(rtb):
+    """reference test/rtree.cpp:98-259 (Erase / Clear): invariants hold while deleting"""
+    keys = make_keys(4, 2000, 5)
+    tree = rtb.RTree(4).insert(keys)
+    rng = np.random.default_rng(6)
+    order = rng.permutation(2000).astype(np.uint32)
+    alive = set(range(2000))
+    for start in range(0, 2000, 250):
+        batch = order[start:start + 250]
+        assert tree.erase_ids(batch) == len(batch)
+        alive -= set(batch.tolist())
+        assert tree.check_invariants() == 0
+        assert tree.size() == len(alive)
+        assert sorted(tree.flatten()["data"].tolist()) == sorted(alive)
+    assert tree.size() == 0 and tree.leaf_level() == 0
+    tree.insert(keys[:100])
+    tree.rebalance()
+    assert tree.size() == 100 and tree.check_invariants() == 0
+    tree.clear()
+    assert tree.size() == 0 and tree.leaf_level() == 0
+    flat = tree.flatten()
+    assert len(flat["nodes"]) == 1 and flat["nodes"][0, 1] == 0
+
+
+@pytest.mark.parametrize("kind", [0, 2, 4, 5, 6])
+def test_flatten_device_layout(rtb, kind):
+    """level-ordered SoA blocks: every node's entries are those of flatten(), in slot order,
+    children renumbered breadth-first, empty slots inverted + RT_INVALID_ID"""
+    capi = rtb.capi
+    keys = make_keys(kind, 2500, 90 + kind)
+    tree = rtb.RTree(kind).insert(keys)
+    flat = tree.flatten()
+    image = tree.flatten_device(ids_from_mapped=True)
+    d = image.desc
+    scalar, dim, is_box, max_entries = O.KINDS[kind]
+    assert (d.dim, d.scalar, d.max_entries) == (dim, scalar, max_entries)
+    assert d.width == (8 if max_entries <= 8 else 16)
+    assert d.key_kind == (capi.RT_KEY_BOX if is_box else capi.RT_KEY_POINT)
+    assert d.leaf_level == flat["leaf_level"] and d.num_levels == d.leaf_level + 1
+    assert d.num_nodes == len(flat["nodes"]) and d.num_values == 2500
+    s = np.dtype(capi.SCALAR_DTYPES[scalar]).itemsize
+    assert d.internal_stride == d.width * (2 * dim * s + 4)
+    assert d.leaf_stride == (d.internal_stride if is_box else d.width * (dim * s + 4))
+    assert d.internal_stride % 16 == 0 and d.leaf_stride % 16 == 0 and d.leaf_offset % 128 == 0
+    assert d.blocks % 256 == 0
+    levels = image.level_node_begin
+    assert levels[0] == 0 and levels[1] == 1 and levels[-1] == d.num_nodes
+    to_dfs = image.bfs_to_dfs
+    assert sorted(to_dfs.tolist()) == list(range(d.num_nodes)) and to_dfs[0] == 0
+    nodes = decode_image(image, capi)
+    next_child = 1
+    for b, (is_leaf, lo, hi, link, valid) in enumerate(nodes):
+        off, size, _ = flat["nodes"][to_dfs[b]]
+        assert valid[:size].all() and not valid[size:].any()
+        bound = flat["children_bound"][off:off + size]
+        assert np.array_equal(lo, bound[:, 0, :]) and np.array_equal(hi, bound[:, 1, :])
+        if is_leaf:
+            assert np.array_equal(link, flat["data"][flat["children"][off:off + size]])
+        else:
+            assert np.array_equal(link, np.arange(next_child, next_child + size))
+            assert np.array_equal(to_dfs[link], flat["children"][off:off + size])
+            next_child += size
+    # data-index ids instead of mapped values
+    image2 = tree.flatten_device(ids_from_mapped=False)
+    leaves = [n for n in decode_image(image2, capi) if n[0]]
+    assert np.array_equal(np.concatenate([n[3] for n in leaves]), np.arange(2500))
+
+
+@needs_ref
+def test_flatten_device_accepts_the_reference_flatten(rtb):
+    """flatten_device() is duck-typed on the reference's flatten_result_t field names"""
+    keys = make_keys(4, 3000, 3)
+    ref = O.RefTree(4).insert(keys).flatten()
+    a = rtb.DeviceImage.from_flat(4, ref.leaf_level, ref.nodes, ref.bounds, ref.children, ref.data)
+    b = rtb.RTree(4).insert(keys).flatten_device()
+    assert np.array_equal(a.blocks(), b.blocks())
+    assert np.array_equal(a.level_node_begin, b.level_node_begin)
+
+
+def test_empty_tree_image(rtb):
+    image = rtb.RTree(4).flatten_device()
+    d = image.desc
+    assert d.num_nodes == 1 and d.leaf_level == 0 and d.num_values == 0
+    (is_leaf, lo, hi, link, valid), = decode_image(image, rtb.capi)
+    assert is_leaf and link.size == 0 and not valid.any()
