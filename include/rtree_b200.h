@@ -51,8 +51,8 @@ extern "C" {
 #define RT_I32 2u
 
 /* rt_tree_desc.key_kind */
-#define RT_KEY_POINT 0u /* leaf blocks store one corner: p[dim][W], id[W]            */
-#define RT_KEY_BOX 1u   /* leaf blocks look like internal ones: lo, hi, id           */
+#define RT_KEY_POINT 0u /* leaf records hold one corner: p_0 .. p_{D-1} id             */
+#define RT_KEY_BOX 1u   /* leaf records look like internal ones: lo/hi pairs, id      */
 
 /* memory spaces */
 #define RT_MEM_HOST 0u
@@ -86,16 +86,25 @@ typedef struct rt_tree rt_tree; /* opaque; owns device memory on ONE GPU */
  *
  * Nodes are renumbered in breadth-first (level) order: node 0 is the root, level l
  * occupies [level_node_begin[l], level_node_begin[l+1]), leaves are the last level.
- * `blocks` holds one fixed-width block per node, W = width slots each:
+ * `blocks` holds one fixed-width block per node, W = width slots each; internal blocks
+ * first (node i at i * internal_stride), then from leaf_offset the leaf blocks (j-th leaf
+ * at leaf_offset + j * leaf_stride).
  *
- *   internal node i :  blocks + i * internal_stride
- *        lo[dim][W] | hi[dim][W] | child[W]      child = node index, RT_INVALID_ID if empty
- *   leaf node j (j counted from the first leaf) :  blocks + leaf_offset + j * leaf_stride
- *        RT_KEY_POINT :  p[dim][W] | id[W]
- *        RT_KEY_BOX   :  lo[dim][W] | hi[dim][W] | id[W]
+ * A slot's RECORD is a run of 32-bit words (a 64-bit scalar takes two):
+ *     internal node, or leaf of a box-keyed tree :  lo_0 hi_0 lo_1 hi_1 ... lo_{D-1} hi_{D-1} link
+ *     leaf of a point-keyed tree                 :  p_0 p_1 ... p_{D-1} link
+ *   link = for a child node: byte offset of the child's block in `blocks`, divided by 16
+ *          (so the root is 0 and "is a leaf" is  link >= leaf_offset / 16);
+ *          for a leaf entry: the 32-bit id reported for a hit;
+ *          RT_INVALID_ID for an empty slot (whose bound is an inverted box).
  *
- * Rows are W consecutive scalars (structure of arrays), every block is 16-byte
- * aligned, empty slots carry an inverted box and RT_INVALID_ID.                      */
+ * A block stores the W records as a structure of arrays OF 16-BYTE VECTORS, so that lane c
+ * of a warp fetches "its" child with one coalesced 128-bit load per row:
+ *     row k (k < words/4)   W x 16 bytes at k*W*16: words 4k..4k+3 of slot 0, of slot 1, ...
+ *     tail (words % 4 = r)  at (words/4)*W*16: W elements of 4 (r=1), 8 (r=2) or 16 (r=3,
+ *                           last word unused) bytes holding the remaining words of each slot
+ * see rt_record_words() / rt_block_bytes() below.  3-D float32, W = 8: an internal block is
+ * two 128-byte rows (256 B), a point leaf exactly one (x y z id per slot, 128 B).        */
 typedef struct rt_tree_desc
 {
   uint32_t abi_version; /* RT_ABI_VERSION */
@@ -108,15 +117,27 @@ typedef struct rt_tree_desc
   uint32_t num_levels;  /* leaf_level + 1 */
   uint32_t num_nodes;
   uint32_t num_values;  /* number of leaf entries */
-  uint32_t internal_stride; /* bytes between internal blocks */
-  uint32_t leaf_stride;     /* bytes between leaf blocks */
-  uint64_t leaf_offset;     /* byte offset of the first leaf block */
+  uint32_t internal_stride; /* == rt_block_bytes(width, rt_record_words(dim, scalar, 1)) */
+  uint32_t leaf_stride;     /* == rt_block_bytes(width, rt_record_words(dim, scalar, key is box)) */
+  uint64_t leaf_offset;     /* byte offset of the first leaf block, a multiple of 128 */
   uint64_t blocks_bytes;
   const void* blocks;
   const uint32_t* level_node_begin; /* [num_levels + 1], host memory */
   uint32_t blocks_memory;           /* RT_MEM_HOST | RT_MEM_DEVICE (same GPU) */
   uint32_t reserved;
 } rt_tree_desc;
+
+/* 32-bit words in a slot record: two corners (or one, for point-key leaves) plus the link */
+static inline uint32_t rt_record_words(uint32_t dim, uint32_t scalar, int two_corners)
+{
+  return (two_corners ? 2u : 1u) * dim * (scalar == RT_F64 ? 2u : 1u) + 1u;
+}
+/* bytes of one block of `width` slots with `words`-word records */
+static inline uint32_t rt_block_bytes(uint32_t width, uint32_t words)
+{
+  static const uint32_t tail_bytes[4] = { 0u, 4u, 8u, 16u };
+  return width * (16u * (words / 4u) + tail_bytes[words % 4u]);
+}
 
 /* CSR hit lists.  The buffers belong to the tree handle and stay valid until the next
  * query on that handle or rt_free().  ids[offsets[q] .. offsets[q+1]) are the hits of

@@ -186,17 +186,19 @@ int check_desc(const rt_tree_desc* d)
   }
   if (d->level_node_begin[1] != 1)
     return fail(RT_E_INVALID, "rt_upload: level 0 must hold exactly the root");
-  const uint32_t s = d->scalar == RT_F64 ? 8u : 4u;
-  const uint32_t internal = d->width * (2 * d->dim * s + 4);
-  const uint32_t leaf = d->key_kind == RT_KEY_BOX ? internal : d->width * (d->dim * s + 4);
-  if (d->internal_stride < internal || d->leaf_stride < leaf || d->internal_stride % 16 || d->leaf_stride % 16
-      || d->leaf_offset % 16)
-    return fail(RT_E_INVALID, "rt_upload: block strides / offsets too small or not 16-byte aligned");
+  const uint32_t internal = rt_block_bytes(d->width, rt_record_words(d->dim, d->scalar, 1));
+  const uint32_t leaf = rt_block_bytes(d->width, rt_record_words(d->dim, d->scalar, d->key_kind == RT_KEY_BOX));
+  if (d->internal_stride != internal || d->leaf_stride != leaf)
+    return fail(RT_E_INVALID, "rt_upload: block strides do not match rt_block_bytes() for this tree");
+  if (d->leaf_offset % 128)
+    return fail(RT_E_INVALID, "rt_upload: leaf_offset must be a multiple of 128");
   const uint32_t leaf_begin = d->level_node_begin[d->leaf_level];
   const uint64_t need_internal = (uint64_t)leaf_begin * d->internal_stride;
   const uint64_t need = d->leaf_offset + (uint64_t)(d->num_nodes - leaf_begin) * d->leaf_stride;
   if (d->leaf_offset < need_internal || d->blocks_bytes < need)
     return fail(RT_E_INVALID, "rt_upload: blocks_bytes smaller than the layout needs");
+  if (need / 16 >= RT_INVALID_ID)
+    return fail(RT_E_INVALID, "rt_upload: tree image larger than 64 GB");
   if (d->num_values >= RT_INVALID_ID)
     return fail(RT_E_INVALID, "rt_upload: too many values");
   return RT_OK;
@@ -301,10 +303,7 @@ int rt_upload(const rt_tree_desc* desc, int device, rt_tree** out)
   t->desc.blocks = t->d_blocks;
   t->desc.blocks_memory = RT_MEM_DEVICE;
   t->dev.blocks = t->d_blocks;
-  t->dev.leaf_offset = desc->leaf_offset;
-  t->dev.internal_stride = desc->internal_stride;
-  t->dev.leaf_stride = desc->leaf_stride;
-  t->dev.leaf_begin = t->levels[desc->leaf_level];
+  t->dev.leaf_link_begin = (uint32_t)(desc->leaf_offset / 16);
   t->dev.num_nodes = desc->num_nodes;
   t->dev.num_levels = desc->num_levels;
   *out = t;

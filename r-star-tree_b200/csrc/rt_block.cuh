@@ -1,0 +1,136 @@
+// rt_block.cuh -- device-side view of the block layout of include/rtree_b200.h, and the
+// small warp / shared-memory primitives the traversal kernels share (internal header).
+#pragma once
+
+#include "rt_common.cuh"
+
+namespace rtb
+{
+
+// ---- slot records: structure of arrays of 16-byte vectors -------------------------------
+// A record of WORDS 32-bit words is stored as WORDS/4 full rows (one uint4 per slot) plus a
+// tail row of 4-, 8- or 16-byte elements; lane `slot` fetches its record with one vector
+// load per row, the W lanes of a group covering W*16 contiguous bytes.
+template <int WORDS, int W>
+struct Record
+{
+  static constexpr int NV = WORDS / 4;
+  static constexpr int R = WORDS % 4;
+  static constexpr int PADDED = (WORDS + 3) / 4 * 4;
+  static constexpr int TAIL_BYTES = R == 0 ? 0 : (R == 1 ? 4 : (R == 2 ? 8 : 16));
+  static constexpr uint32_t BYTES = W * (16 * NV + TAIL_BYTES);
+
+  __device__ __forceinline__ static void load(const unsigned char* __restrict__ blk, int slot, uint32_t (&w)[PADDED])
+  {
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+    {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(blk + k * W * 16) + slot);
+      w[4 * k + 0] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
+    }
+    const unsigned char* tail = blk + NV * W * 16;
+    if (R == 1)
+    {
+      w[4 * NV] = __ldg(reinterpret_cast<const uint32_t*>(tail) + slot);
+    }
+    else if (R == 2)
+    {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(tail) + slot);
+      w[4 * NV] = v.x, w[4 * NV + 1] = v.y;
+    }
+    else if (R == 3)
+    {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(tail) + slot);
+      w[4 * NV] = v.x, w[4 * NV + 1] = v.y, w[4 * NV + 2] = v.z, w[4 * NV + 3] = v.w;
+    }
+  }
+};
+
+template <typename S>
+struct ScalarWords;
+template <>
+struct ScalarWords<float>
+{
+  static constexpr int N = 1;
+  __device__ __forceinline__ static float get(const uint32_t* w) { return __uint_as_float(w[0]); }
+};
+template <>
+struct ScalarWords<int32_t>
+{
+  static constexpr int N = 1;
+  __device__ __forceinline__ static int32_t get(const uint32_t* w) { return (int32_t)w[0]; }
+};
+template <>
+struct ScalarWords<double>
+{
+  static constexpr int N = 2;
+  __device__ __forceinline__ static double get(const uint32_t* w) { return __hiloint2double((int)w[1], (int)w[0]); }
+};
+
+// Load the record of `slot` from the block at `blk` and split it into corners + link.
+// Point-keyed leaves store one corner (lo == hi).
+template <typename S, int D, int W, bool BOXKEY>
+__device__ __forceinline__ void load_entry(const unsigned char* __restrict__ blk, int slot, bool is_leaf,
+                                           S (&lo)[D], S (&hi)[D], uint32_t& link)
+{
+  constexpr int SW = ScalarWords<S>::N;
+  using Two = Record<2 * D * SW + 1, W>;
+  using One = Record<D * SW + 1, W>;
+  if (!BOXKEY && is_leaf)
+  {
+    uint32_t w[One::PADDED];
+    One::load(blk, slot, w);
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      lo[d] = hi[d] = ScalarWords<S>::get(w + d * SW);
+    link = w[D * SW];
+  }
+  else
+  {
+    uint32_t w[Two::PADDED];
+    Two::load(blk, slot, w);
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+    {
+      lo[d] = ScalarWords<S>::get(w + 2 * d * SW);
+      hi[d] = ScalarWords<S>::get(w + (2 * d + 1) * SW);
+    }
+    link = w[2 * D * SW];
+  }
+}
+
+// ---- shared memory through 32-bit addresses (keeps the address math out of the loop) ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p)
+{
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// ascending bitonic sort of one value per lane
+__device__ __forceinline__ uint32_t warp_sort32(uint32_t v, int lane)
+{
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1)
+  {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1)
+    {
+      const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, v, j);
+      const bool ascending = (lane & k) == 0;
+      const bool lower = (lane & j) == 0;
+      v = (lower == ascending) ? min(v, other) : max(v, other);
+    }
+  }
+  return v;
+}
+
+} // namespace rtb

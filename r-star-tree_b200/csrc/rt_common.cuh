@@ -15,14 +15,13 @@
 namespace rtb
 {
 
-// The uploaded tree as kernels see it (see rt_tree_desc in include/rtree_b200.h).
+// The uploaded tree as kernels see it (layout: rt_tree_desc in include/rtree_b200.h).
+// Nodes are named by the byte offset of their block divided by 16 ("link"): the root is
+// link 0 and a link at or above leaf_link_begin names a leaf block.
 struct TreeDev
 {
   const unsigned char* blocks; // internal blocks, then (at leaf_offset) leaf blocks
-  unsigned long long leaf_offset;
-  uint32_t internal_stride;
-  uint32_t leaf_stride;
-  uint32_t leaf_begin; // first leaf node index == number of internal nodes
+  uint32_t leaf_link_begin;    // leaf_offset / 16
   uint32_t num_nodes;
   uint32_t num_levels;
 };

@@ -10,8 +10,9 @@
 //
 // Mapping.  One warp answers one query at a time.  A block is W (8 or 16) slots wide, so
 // the 32 lanes cover G = 32/W nodes per step: lane = (group g, slot c) loads child c of
-// the g-th node popped from the warp's stack -- one 4/8-byte load per row, the W lanes of
-// a group reading one contiguous, sector-aligned row (SoA), i.e. fully coalesced.  The
+// the g-th node popped from the warp's stack -- one 128-bit load per 4 record words, the
+// W lanes of a group reading W*16 contiguous bytes (rt_block.cuh), i.e. fully coalesced:
+// a 3-D float internal node is two such loads, a point leaf one.  The
 // per-axis interval tests run in registers, __ballot_sync gathers the W-bit hit masks of
 // all G nodes at once, and __popc over the lower lanes gives every hit lane its slot on
 // the stack (children to descend) or in the hit list (leaf entries), so both compactions
@@ -31,34 +32,11 @@
 // PASS_WRITE: hit ids go to their final CSR position; short lists are sorted in the warp.
 #pragma once
 
+#include "rt_block.cuh"
 #include "rt_common.cuh"
 
 namespace rtb
 {
-
-template <typename S>
-__device__ __forceinline__ S ld_ro(const S* p)
-{
-  return __ldg(p);
-}
-
-// ascending bitonic sort of one value per lane
-__device__ __forceinline__ uint32_t warp_sort32(uint32_t v, int lane)
-{
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1)
-  {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1)
-    {
-      const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, v, j);
-      const bool ascending = (lane & k) == 0;
-      const bool lower = (lane & j) == 0;
-      v = (lower == ascending) ? min(v, other) : max(v, other);
-    }
-  }
-  return v;
-}
 
 template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS>
 __global__ void __launch_bounds__(TRAVERSE_THREADS)
@@ -70,21 +48,15 @@ box_traverse_kernel(const BoxLaunch p)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int slot = lane % W;
-  const int grp = lane / W;
+  const uint32_t grp = lane / W;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
   const uint32_t stack_cap = 32u * p.tree.num_levels;
-  uint32_t* stack = smem + warp * (stack_cap + HIT_BUF);
-  uint32_t* hitbuf = stack + stack_cap;
+  const uint32_t stack = smem_addr(smem + warp * (stack_cap + HIT_BUF)); // 32-bit shared addresses
+  const uint32_t hitbuf = stack + stack_cap * 4u;
 
-  const unsigned char* __restrict__ int_base = p.tree.blocks;
-  const unsigned char* __restrict__ leaf_base = p.tree.blocks + p.tree.leaf_offset;
-  const uint32_t leaf_begin = p.tree.leaf_begin;
-  const uint32_t int_stride = p.tree.internal_stride;
-  const uint32_t leaf_stride = p.tree.leaf_stride;
-  constexpr uint32_t LINK_OFF_INTERNAL = 2u * D * W * sizeof(S);
-  constexpr uint32_t LINK_OFF_LEAF = (BOXKEY ? 2u : 1u) * D * W * sizeof(S);
-
+  const unsigned char* __restrict__ blocks = p.tree.blocks;
+  const uint32_t leaf_link_begin = p.tree.leaf_link_begin;
   const S* __restrict__ queries = static_cast<const S*>(p.queries);
 
   unsigned long long visits_int = 0, visits_leaf = 0;
@@ -109,8 +81,8 @@ box_traverse_kernel(const BoxLaunch p)
 #pragma unroll
       for (int d = 0; d < D; ++d)
       {
-        qlo[d] = ld_ro(queries + qi * (2 * D) + d);
-        qhi[d] = ld_ro(queries + qi * (2 * D) + D + d);
+        qlo[d] = __ldg(queries + qi * (2 * D) + d);
+        qhi[d] = __ldg(queries + qi * (2 * D) + D + d);
       }
 
       unsigned long long out_base = 0;
@@ -126,38 +98,26 @@ box_traverse_kernel(const BoxLaunch p)
       uint32_t count = 0;
       uint32_t sp = 1;
       if (lane == 0)
-        stack[0] = 0; // the root; its own bound is never tested (reference rtree.hpp:984)
+        sts_u32(stack, 0u); // the root; its own bound is never tested (reference rtree.hpp:984)
       __syncwarp();
 
       while (sp > 0)
       {
         const uint32_t take = min(sp, (uint32_t)G);
         sp -= take;
-        const bool active = (uint32_t)grp < take;
+        const bool active = grp < take;
         uint32_t node = RT_INVALID_ID;
         if (active)
-          node = stack[sp + grp];
+          node = lds_u32(stack + (sp + grp) * 4u);
         __syncwarp();
 
-        const bool is_leaf = node >= leaf_begin;
-        const unsigned char* blk = is_leaf
-                                       ? leaf_base + (unsigned long long)(node - leaf_begin) * leaf_stride
-                                       : int_base + (unsigned long long)node * int_stride;
-        const bool one_corner = !BOXKEY && is_leaf;
-
+        const bool is_leaf = node >= leaf_link_begin;
         uint32_t link = RT_INVALID_ID;
         bool hit = false;
         if (active)
         {
-          const S* row = reinterpret_cast<const S*>(blk) + slot;
-          link = ld_ro(reinterpret_cast<const uint32_t*>(blk + (is_leaf ? LINK_OFF_LEAF : LINK_OFF_INTERNAL)) + slot);
           S lo[D], hi[D];
-#pragma unroll
-          for (int d = 0; d < D; ++d)
-            lo[d] = ld_ro(row + d * W);
-#pragma unroll
-          for (int d = 0; d < D; ++d)
-            hi[d] = one_corner ? lo[d] : ld_ro(row + (D + d) * W);
+          load_entry<S, D, W, BOXKEY>(blocks + (unsigned long long)node * 16u, slot, is_leaf, lo, hi, link);
           hit = link != RT_INVALID_ID;
 #pragma unroll
           for (int d = 0; d < D; ++d)
@@ -191,7 +151,7 @@ box_traverse_kernel(const BoxLaunch p)
 
         // children to descend: compact onto the stack in lane order (keeps it level-sorted)
         if (hit && !is_leaf)
-          stack[sp + __popc(m_int & lt_mask)] = link;
+          sts_u32(stack + (sp + __popc(m_int & lt_mask)) * 4u, link);
         sp += __popc(m_int);
 
         // leaf entries that satisfy the predicate
@@ -205,7 +165,7 @@ box_traverse_kernel(const BoxLaunch p)
               if (buffered)
               {
                 if (at < HIT_BUF)
-                  hitbuf[at] = link;
+                  sts_u32(hitbuf + at * 4u, link);
               }
               else if (PASS == PASS_WRITE && at < expect)
               {
@@ -251,7 +211,7 @@ box_traverse_kernel(const BoxLaunch p)
           }
           if (slab_left >= count)
           {
-            uint32_t v = ((uint32_t)lane < count) ? hitbuf[lane] : RT_INVALID_ID;
+            uint32_t v = ((uint32_t)lane < count) ? lds_u32(hitbuf + lane * 4u) : RT_INVALID_ID;
             if (p.sorted)
               v = warp_sort32(v, lane);
             if ((uint32_t)lane < count)
@@ -273,7 +233,7 @@ box_traverse_kernel(const BoxLaunch p)
       {
         if (buffered)
         {
-          uint32_t v = ((uint32_t)lane < count) ? hitbuf[lane] : RT_INVALID_ID;
+          uint32_t v = ((uint32_t)lane < count) ? lds_u32(hitbuf + lane * 4u) : RT_INVALID_ID;
           v = warp_sort32(v, lane);
           if ((uint32_t)lane < count && (uint32_t)lane < expect)
             p.ids[out_base + lane] = v;

@@ -18,8 +18,8 @@
 // (t, id) can never be pruned because every ancestor bound has t_entry <= t.
 #pragma once
 
+#include "rt_block.cuh"
 #include "rt_common.cuh"
-#include "rt_traverse_box.cuh"
 
 namespace rtb
 {
@@ -44,20 +44,15 @@ ray_traverse_kernel(const RayLaunch p)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int slot = lane % W;
-  const int grp = lane / W;
+  const uint32_t grp = lane / W;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
   const uint32_t stack_cap = 32u * p.tree.num_levels;
-  uint32_t* stack = smem + warp * (stack_cap + HIT_BUF);
-  uint32_t* hitbuf = stack + stack_cap;
+  const uint32_t stack = smem_addr(smem + warp * (stack_cap + HIT_BUF));
+  const uint32_t hitbuf = stack + stack_cap * 4u;
 
-  const unsigned char* __restrict__ int_base = p.tree.blocks;
-  const unsigned char* __restrict__ leaf_base = p.tree.blocks + p.tree.leaf_offset;
-  const uint32_t leaf_begin = p.tree.leaf_begin;
-  const uint32_t int_stride = p.tree.internal_stride;
-  const uint32_t leaf_stride = p.tree.leaf_stride;
-  constexpr uint32_t LINK_OFF_INTERNAL = 2u * D * W * sizeof(float);
-  constexpr uint32_t LINK_OFF_LEAF = (BOXKEY ? 2u : 1u) * D * W * sizeof(float);
+  const unsigned char* __restrict__ blocks = p.tree.blocks;
+  const uint32_t leaf_link_begin = p.tree.leaf_link_begin;
 
   unsigned long long visits_int = 0, visits_leaf = 0, rays_hit = 0;
 
@@ -99,39 +94,27 @@ ray_traverse_kernel(const RayLaunch p)
       uint32_t count = 0;
       uint32_t sp = 1;
       if (lane == 0)
-        stack[0] = 0;
+        sts_u32(stack, 0u);
       __syncwarp();
 
       while (sp > 0)
       {
         const uint32_t take = min(sp, (uint32_t)G);
         sp -= take;
-        const bool active = (uint32_t)grp < take;
+        const bool active = grp < take;
         uint32_t node = RT_INVALID_ID;
         if (active)
-          node = stack[sp + grp];
+          node = lds_u32(stack + (sp + grp) * 4u);
         __syncwarp();
 
-        const bool is_leaf = node >= leaf_begin;
-        const unsigned char* blk = is_leaf
-                                       ? leaf_base + (unsigned long long)(node - leaf_begin) * leaf_stride
-                                       : int_base + (unsigned long long)node * int_stride;
-        const bool one_corner = !BOXKEY && is_leaf;
-
+        const bool is_leaf = node >= leaf_link_begin;
         uint32_t link = RT_INVALID_ID;
         bool hit = false;
         float t0 = 0.0f;
         if (active)
         {
-          const float* row = reinterpret_cast<const float*>(blk) + slot;
-          link = __ldg(reinterpret_cast<const uint32_t*>(blk + (is_leaf ? LINK_OFF_LEAF : LINK_OFF_INTERNAL)) + slot);
           float lo[D], hi[D];
-#pragma unroll
-          for (int d = 0; d < D; ++d)
-            lo[d] = __ldg(row + d * W);
-#pragma unroll
-          for (int d = 0; d < D; ++d)
-            hi[d] = one_corner ? lo[d] : __ldg(row + (D + d) * W);
+          load_entry<float, D, W, BOXKEY>(blocks + (unsigned long long)node * 16u, slot, is_leaf, lo, hi, link);
           float t1 = tmax;
 #pragma unroll
           for (int d = 0; d < D; ++d)
@@ -160,7 +143,7 @@ ray_traverse_kernel(const RayLaunch p)
         }
 
         if (hit && !is_leaf)
-          stack[sp + __popc(m_int & lt_mask)] = link;
+          sts_u32(stack + (sp + __popc(m_int & lt_mask)) * 4u, link);
         sp += __popc(m_int);
 
         if (m_leaf != 0)
@@ -193,7 +176,7 @@ ray_traverse_kernel(const RayLaunch p)
               if (buffered)
               {
                 if (at < HIT_BUF)
-                  hitbuf[at] = link;
+                  sts_u32(hitbuf + at * 4u, link);
               }
               else if (at < expect)
               {
@@ -215,7 +198,7 @@ ray_traverse_kernel(const RayLaunch p)
       {
         if (buffered)
         {
-          uint32_t v = ((uint32_t)lane < count) ? hitbuf[lane] : RT_INVALID_ID;
+          uint32_t v = ((uint32_t)lane < count) ? lds_u32(hitbuf + lane * 4u) : RT_INVALID_ID;
           v = warp_sort32(v, lane);
           if ((uint32_t)lane < count && (uint32_t)lane < expect)
             p.ids[out_base + lane] = v;

@@ -8,11 +8,14 @@
 //
 //   * nodes renumbered breadth-first, so a level is one contiguous range, siblings
 //     are adjacent and the top of the tree is a small prefix of the buffer;
-//   * one fixed-width block per node, W = MAX_ENTRIES rounded up to 8 or 16 slots,
-//     structure-of-arrays by axis:  lo[dim][W] | hi[dim][W] | child[W]; a warp lane
-//     reads "its" child with one coalesced load per row;
-//   * leaves of point-keyed trees keep one corner only:  p[dim][W] | id[W];
+//   * one fixed-width block per node, W = MAX_ENTRIES rounded up to 8 or 16 slots; a
+//     slot's record is  lo_0 hi_0 ... lo_{D-1} hi_{D-1} link  (32-bit words), stored as a
+//     structure of arrays of 16-byte vectors: row k holds words 4k..4k+3 of all W slots,
+//     so a warp lane reads "its" child with one coalesced 128-bit load per row;
+//   * leaves of point-keyed trees keep one corner only:  p_0 .. p_{D-1} id;
+//   * a child link is the child block's byte offset / 16, so the kernels never multiply;
 //   * empty slots hold an inverted box and RT_INVALID_ID, so lanes need no size test.
+// The exact layout is specified in include/rtree_b200.h (rt_tree_desc).
 //
 // The result is a POD descriptor (rt_tree_desc, include/rtree_b200.h) plus one
 // contiguous 256-byte aligned host buffer; hand desc() to rt_upload().
@@ -207,8 +210,10 @@ device_tree_t flatten_device(FlattenResult const& flat, id_source ids = id_sourc
   out.key_kind = KeyIsBox ? RT_KEY_BOX : RT_KEY_POINT;
   out.leaf_level = flat.leaf_level;
   out.num_values = static_cast<std::uint32_t>(flat.data.size());
-  out.internal_stride = W * (2 * D * sizeof(scalar) + 4);
-  out.leaf_stride = KeyIsBox ? out.internal_stride : W * (D * sizeof(scalar) + 4);
+  const std::uint32_t internal_words = rt_record_words(D, out.scalar, 1);
+  const std::uint32_t leaf_words = rt_record_words(D, out.scalar, KeyIsBox ? 1 : 0);
+  out.internal_stride = rt_block_bytes(W, internal_words);
+  out.leaf_stride = rt_block_bytes(W, leaf_words);
 
   // ---- breadth-first renumbering (levels are implicit in the flat form: a node is a
   //      leaf iff it is leaf_level steps below node 0, reference test/rtree.cpp:383)
@@ -241,12 +246,33 @@ device_tree_t flatten_device(FlattenResult const& flat, id_source ids = id_sourc
   out.leaf_offset = (internal_bytes + 127) / 128 * 128;
   out.blocks = detail::aligned_bytes(out.leaf_offset + std::uint64_t(n_leaves) * out.leaf_stride);
 
+  if ((out.leaf_offset + std::uint64_t(n_leaves) * out.leaf_stride) / 16 >= RT_INVALID_ID)
+    throw std::length_error("flatten_device: tree image larger than 64 GB");
+
   const scalar empty_lo = std::numeric_limits<scalar>::has_infinity
                               ? std::numeric_limits<scalar>::infinity()
                               : std::numeric_limits<scalar>::max();
   const scalar empty_hi = std::numeric_limits<scalar>::has_infinity
                               ? -std::numeric_limits<scalar>::infinity()
                               : std::numeric_limits<scalar>::lowest();
+  constexpr std::uint32_t SW = sizeof(scalar) / 4; // words per scalar
+
+  // word j of slot c of a block with `words`-word records (see include/rtree_b200.h)
+  auto word_at = [](unsigned char* block, std::uint32_t words, std::uint32_t c, std::uint32_t j) -> std::uint32_t*
+  {
+    static const std::uint32_t tail_bytes[4] = { 0u, 4u, 8u, 16u };
+    const std::uint32_t full = words / 4;
+    if (j < 4 * full)
+      return reinterpret_cast<std::uint32_t*>(block + (j / 4) * W * 16 + c * 16 + (j % 4) * 4);
+    return reinterpret_cast<std::uint32_t*>(block + full * W * 16 + c * tail_bytes[words % 4] + (j - 4 * full) * 4);
+  };
+  auto put_scalar = [&](unsigned char* block, std::uint32_t words, std::uint32_t c, std::uint32_t j, scalar v)
+  {
+    std::uint32_t raw[SW];
+    std::memcpy(raw, &v, sizeof v);
+    for (std::uint32_t k = 0; k < SW; ++k)
+      *word_at(block, words, c, j + k) = raw[k];
+  };
 
   // children of consecutive breadth-first nodes are consecutive breadth-first nodes
   std::uint32_t next_child = 1;
@@ -258,43 +284,49 @@ device_tree_t flatten_device(FlattenResult const& flat, id_source ids = id_sourc
     unsigned char* block = is_leaf ? base + out.leaf_offset + std::uint64_t(b - leaf_begin) * out.leaf_stride
                                    : base + std::uint64_t(b) * out.internal_stride;
     const bool one_corner = is_leaf && !KeyIsBox;
-    scalar* lo = reinterpret_cast<scalar*>(block);
-    scalar* hi = one_corner ? nullptr : lo + D * W;
-    std::uint32_t* link = reinterpret_cast<std::uint32_t*>(block + (one_corner ? D : 2 * D) * W * sizeof(scalar));
-    if (is_leaf && node.size > MaxEntries)
-      throw std::invalid_argument("flatten_device: leaf wider than MAX_ENTRIES");
+    const std::uint32_t words = is_leaf ? leaf_words : internal_words;
+    if (node.size > MaxEntries)
+      throw std::invalid_argument("flatten_device: node wider than MAX_ENTRIES");
     for (std::uint32_t c = 0; c < W; ++c)
     {
-      if (c < node.size)
+      const bool used = c < node.size;
+      std::uint32_t link = RT_INVALID_ID;
+      for (std::uint32_t d = 0; d < D; ++d)
       {
-        geometry_type const& g = flat.children_bound[node.offset + c];
-        for (std::uint32_t d = 0; d < D; ++d)
+        scalar lo = empty_lo, hi = empty_hi;
+        if (used)
         {
-          lo[d * W + c] = gtraits::min_point(g, static_cast<int>(d));
-          if (hi != nullptr)
-            hi[d * W + c] = gtraits::max_point(g, static_cast<int>(d));
+          geometry_type const& g = flat.children_bound[node.offset + c];
+          lo = gtraits::min_point(g, static_cast<int>(d));
+          hi = gtraits::max_point(g, static_cast<int>(d));
         }
-        if (is_leaf)
+        if (one_corner)
         {
-          const std::uint32_t data_index = flat.children[node.offset + c];
-          link[c] = (ids == id_source::mapped_value) ? detail::mapped_as_id(flat.data[data_index])
-                                                     : data_index;
+          put_scalar(block, words, c, d * SW, lo);
         }
         else
         {
-          link[c] = next_child++;
+          put_scalar(block, words, c, 2 * d * SW, lo);
+          put_scalar(block, words, c, (2 * d + 1) * SW, hi);
         }
       }
-      else
+      if (used)
       {
-        for (std::uint32_t d = 0; d < D; ++d)
+        if (is_leaf)
         {
-          lo[d * W + c] = empty_lo;
-          if (hi != nullptr)
-            hi[d * W + c] = empty_hi;
+          const std::uint32_t data_index = flat.children[node.offset + c];
+          link = (ids == id_source::mapped_value) ? detail::mapped_as_id(flat.data[data_index]) : data_index;
         }
-        link[c] = RT_INVALID_ID;
+        else
+        {
+          const std::uint32_t child = next_child++;
+          const std::uint64_t child_offset
+              = child >= leaf_begin ? out.leaf_offset + std::uint64_t(child - leaf_begin) * out.leaf_stride
+                                    : std::uint64_t(child) * out.internal_stride;
+          link = static_cast<std::uint32_t>(child_offset / 16);
+        }
       }
+      *word_at(block, words, c, words - 1) = link;
     }
   }
   return out;

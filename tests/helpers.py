@@ -2,32 +2,68 @@
 import numpy as np
 
 
+TAIL_BYTES = (0, 4, 8, 16)
+
+
+def record_words(dim, scalar_bytes, two_corners):
+    return (2 if two_corners else 1) * dim * (scalar_bytes // 4) + 1
+
+
+def block_bytes(width, words):
+    return width * (16 * (words // 4) + TAIL_BYTES[words % 4])
+
+
+def block_records(raw, start, width, words):
+    """uint32 [width][words]: the slot records of the block at byte offset `start`
+    (rows of 16-byte vectors + tail row, include/rtree_b200.h)."""
+    full = words // 4
+    rec = np.zeros((width, words), np.uint32)
+    for k in range(full):
+        row = np.frombuffer(raw[start + k * width * 16:start + (k + 1) * width * 16].tobytes(), np.uint32)
+        rec[:, 4 * k:4 * k + 4] = row.reshape(width, 4)
+    r = words % 4
+    if r:
+        eb = TAIL_BYTES[r]
+        t0 = start + full * width * 16
+        tail = np.frombuffer(raw[t0:t0 + width * eb].tobytes(), np.uint32).reshape(width, eb // 4)
+        rec[:, 4 * full:] = tail[:, :r]
+    return rec
+
+
 def decode_image(image, capi):
     """Decode RTree::flatten_device() output (rt_tree_desc + blocks) into, per node in
-    breadth-first order: (is_leaf, lo[n][dim], hi[n][dim], link[n]) with empty slots removed."""
+    breadth-first order: (is_leaf, lo[n][dim], hi[n][dim], link[n], valid[W]) with empty slots
+    removed from lo / hi / link."""
     d = image.desc
     dt = np.dtype(capi.SCALAR_DTYPES[d.scalar])
-    W, D = d.width, d.dim
+    W, D, sb = d.width, d.dim, dt.itemsize
     raw = image.blocks()
     levels = image.level_node_begin
     leaf_begin = int(levels[d.leaf_level])
     out = []
     for b in range(d.num_nodes):
         is_leaf = b >= leaf_begin
-        if is_leaf:
-            start = d.leaf_offset + (b - leaf_begin) * d.leaf_stride
-        else:
-            start = b * d.internal_stride
+        start = d.leaf_offset + (b - leaf_begin) * d.leaf_stride if is_leaf else b * d.internal_stride
         one_corner = is_leaf and d.key_kind == capi.RT_KEY_POINT
-        rows = D if one_corner else 2 * D
-        vals = np.frombuffer(raw[start:start + rows * W * dt.itemsize].tobytes(), dt).reshape(rows, W)
-        link = np.frombuffer(raw[start + rows * W * dt.itemsize:start + rows * W * dt.itemsize + 4 * W].tobytes(),
-                             np.uint32)
+        words = record_words(D, sb, not one_corner)
+        rec = block_records(raw, start, W, words)
+        link = rec[:, words - 1]
         valid = link != capi.RT_INVALID_ID
-        lo = vals[:D, valid].T
-        hi = lo if one_corner else vals[D:, valid].T
+        scalars = np.ascontiguousarray(rec[:, :words - 1]).view(dt)   # [W][corners*D]
+        if one_corner:
+            lo = hi = scalars[valid]
+        else:
+            lo, hi = scalars[valid][:, 0::2], scalars[valid][:, 1::2]
         out.append((is_leaf, lo, hi, link[valid], valid))
     return out
+
+
+def node_link(image, b):
+    """the link (block byte offset / 16) that names breadth-first node b"""
+    d = image.desc
+    leaf_begin = int(image.level_node_begin[d.leaf_level])
+    off = d.leaf_offset + (b - leaf_begin) * d.leaf_stride if b >= leaf_begin else b * d.internal_stride
+    return off // 16
 
 
 def csr_equal(a, b):

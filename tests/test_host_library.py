@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracles as O
-from helpers import decode_image, csr_equal
+from helpers import decode_image, csr_equal, node_link, record_words, block_bytes
 
 needs_ref = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/libref_oracle.so not built")
 
@@ -117,8 +117,10 @@ def test_flatten_device_layout(rtb, kind):
     assert d.leaf_level == flat["leaf_level"] and d.num_levels == d.leaf_level + 1
     assert d.num_nodes == len(flat["nodes"]) and d.num_values == 2500
     s = np.dtype(capi.SCALAR_DTYPES[scalar]).itemsize
-    assert d.internal_stride == d.width * (2 * dim * s + 4)
-    assert d.leaf_stride == (d.internal_stride if is_box else d.width * (dim * s + 4))
+    assert d.internal_stride == block_bytes(d.width, record_words(dim, s, True))
+    assert d.leaf_stride == block_bytes(d.width, record_words(dim, s, is_box))
+    if (kind, d.width) == (4, 8):
+        assert (d.internal_stride, d.leaf_stride) == (256, 128)   # 3-D f32: 2 rows / 1 row of 128 B
     assert d.internal_stride % 16 == 0 and d.leaf_stride % 16 == 0 and d.leaf_offset % 128 == 0
     assert d.blocks % 256 == 0
     levels = image.level_node_begin
@@ -135,8 +137,9 @@ def test_flatten_device_layout(rtb, kind):
         if is_leaf:
             assert np.array_equal(link, flat["data"][flat["children"][off:off + size]])
         else:
-            assert np.array_equal(link, np.arange(next_child, next_child + size))
-            assert np.array_equal(to_dfs[link], flat["children"][off:off + size])
+            kids = np.arange(next_child, next_child + size)
+            assert np.array_equal(link, [node_link(image, k) for k in kids])
+            assert np.array_equal(to_dfs[kids], flat["children"][off:off + size])
             next_child += size
     # data-index ids instead of mapped values
     image2 = tree.flatten_device(ids_from_mapped=False)
