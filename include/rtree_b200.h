@@ -91,8 +91,12 @@ typedef struct rt_tree rt_tree; /* opaque; owns device memory on ONE GPU */
  * at leaf_offset + j * leaf_stride).
  *
  * A slot's RECORD is a run of 32-bit words (a 64-bit scalar takes two):
- *     internal node, or leaf of a box-keyed tree :  lo_0 hi_0 lo_1 hi_1 ... lo_{D-1} hi_{D-1} link
- *     leaf of a point-keyed tree                 :  p_0 p_1 ... p_{D-1} link
+ *     internal node, or leaf of a box-keyed tree :  lo_0 .. lo_{D-1}  link  hi_0 .. hi_{D-1}
+ *     leaf of a point-keyed tree                 :  p_0 .. p_{D-1}  link
+ *   (with 64-bit scalars one unused word follows the link of a two-corner record, so that
+ *   the hi corner stays 8-byte aligned).  The one-corner record is a prefix of the
+ *   two-corner one: a lane reads "lo corner + link" the same way in both, and only
+ *   internal nodes fetch the hi corner.
  *   link = for a child node: byte offset of the child's block in `blocks`, divided by 16
  *          (so the root is 0 and "is a leaf" is  link >= leaf_offset / 16);
  *          for a leaf entry: the 32-bit id reported for a hit;
@@ -104,7 +108,8 @@ typedef struct rt_tree rt_tree; /* opaque; owns device memory on ONE GPU */
  *     tail (words % 4 = r)  at (words/4)*W*16: W elements of 4 (r=1), 8 (r=2) or 16 (r=3,
  *                           last word unused) bytes holding the remaining words of each slot
  * see rt_record_words() / rt_block_bytes() below.  3-D float32, W = 8: an internal block is
- * two 128-byte rows (256 B), a point leaf exactly one (x y z id per slot, 128 B).        */
+ * two 128-byte rows (lo_x lo_y lo_z link | hi_x hi_y hi_z -, 256 B), a point leaf exactly
+ * one (x y z id per slot, 128 B).                                                         */
 typedef struct rt_tree_desc
 {
   uint32_t abi_version; /* RT_ABI_VERSION */
@@ -127,10 +132,11 @@ typedef struct rt_tree_desc
   uint32_t reserved;
 } rt_tree_desc;
 
-/* 32-bit words in a slot record: two corners (or one, for point-key leaves) plus the link */
+/* 32-bit words in a slot record: corners + link (+ alignment word, see above) */
 static inline uint32_t rt_record_words(uint32_t dim, uint32_t scalar, int two_corners)
 {
-  return (two_corners ? 2u : 1u) * dim * (scalar == RT_F64 ? 2u : 1u) + 1u;
+  const uint32_t sw = scalar == RT_F64 ? 2u : 1u;
+  return two_corners ? 2u * dim * sw + sw : dim * sw + 1u;
 }
 /* bytes of one block of `width` slots with `words`-word records */
 static inline uint32_t rt_block_bytes(uint32_t width, uint32_t words)
@@ -180,6 +186,7 @@ typedef struct rt_stats
   uint64_t visits_internal;
   uint64_t visits_leaf;
   uint64_t algorithmic_bytes; /* SURVEY.md 8d formula on the visit totals */
+  uint64_t traverse_steps;    /* warp loop iterations; visits / (steps * 32/W) = lane-group use */
 } rt_stats;
 
 /* Copy the tree image to `device` (cudaSetDevice(device) is called by every entry

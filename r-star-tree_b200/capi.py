@@ -65,7 +65,7 @@ class RtStats(C.Structure):
                 ("traverse_ms", C.c_float), ("finish_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("kernel_launches", C.c_uint32), ("deferred_queries", C.c_uint32),
                 ("visits_internal", C.c_uint64), ("visits_leaf", C.c_uint64),
-                ("algorithmic_bytes", C.c_uint64)]
+                ("algorithmic_bytes", C.c_uint64), ("traverse_steps", C.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

@@ -117,11 +117,11 @@ struct Counters
 {
   unsigned long long work;        // query chunk cursor
   unsigned long long stash_cursor;
-  unsigned long long visits[3];   // internal visits, leaf visits, rays with a hit
+  unsigned long long visits[4];   // internal visits, leaf visits, rays with a hit, loop steps
   unsigned long long total;       // filled by copying offsets[n]
   uint32_t deferred;
   uint32_t big;
-  uint32_t pad[2];
+
 };
 static_assert(sizeof(Counters) == 64, "Counters layout");
 
@@ -603,6 +603,7 @@ int rt_query_boxes(rt_tree* t, const void* boxes, uint64_t n, uint32_t mode, uin
   {
     s.visits_internal = hc.visits[0];
     s.visits_leaf = hc.visits[1];
+    s.traverse_steps = hc.visits[3];
     s.algorithmic_bytes = algorithmic_bytes_boxes(t, n, total, hc.visits[0], hc.visits[1]);
   }
   return RT_OK;
@@ -807,6 +808,7 @@ int rt_query_rays(rt_tree* t, const float* rays, uint64_t n, uint32_t mode, uint
   {
     s.visits_internal = hc.visits[0];
     s.visits_leaf = hc.visits[1];
+    s.traverse_steps = hc.visits[3];
     const uint64_t M = t->desc.max_entries;
     const uint64_t b_int = M * (2 * 3 * 4 + 4);
     const uint64_t b_leaf = t->desc.key_kind == RT_KEY_BOX ? b_int : M * (3 * 4 + 4);

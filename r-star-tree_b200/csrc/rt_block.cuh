@@ -20,27 +20,30 @@ struct Record
   static constexpr int TAIL_BYTES = R == 0 ? 0 : (R == 1 ? 4 : (R == 2 ? 8 : 16));
   static constexpr uint32_t BYTES = W * (16 * NV + TAIL_BYTES);
 
-  __device__ __forceinline__ static void load(const unsigned char* __restrict__ blk, int slot, uint32_t (&w)[PADDED])
+  // `lane_blk` = block address + slot * 16 (the lane's element in a 16-byte row)
+  __device__ __forceinline__ static void load(const unsigned char* __restrict__ lane_blk, int slot,
+                                              uint32_t (&w)[PADDED])
   {
 #pragma unroll
     for (int k = 0; k < NV; ++k)
     {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(blk + k * W * 16) + slot);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(lane_blk + k * W * 16));
       w[4 * k + 0] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
     }
-    const unsigned char* tail = blk + NV * W * 16;
+    // tail elements are TAIL_BYTES wide: step back from the 16-byte lane offset
+    const unsigned char* tail = lane_blk + NV * W * 16 - slot * (16 - TAIL_BYTES);
     if (R == 1)
     {
-      w[4 * NV] = __ldg(reinterpret_cast<const uint32_t*>(tail) + slot);
+      w[4 * NV] = __ldg(reinterpret_cast<const uint32_t*>(tail));
     }
     else if (R == 2)
     {
-      const uint2 v = __ldg(reinterpret_cast<const uint2*>(tail) + slot);
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(tail));
       w[4 * NV] = v.x, w[4 * NV + 1] = v.y;
     }
     else if (R == 3)
     {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(tail) + slot);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(tail));
       w[4 * NV] = v.x, w[4 * NV + 1] = v.y, w[4 * NV + 2] = v.z, w[4 * NV + 3] = v.w;
     }
   }
@@ -67,14 +70,16 @@ struct ScalarWords<double>
   __device__ __forceinline__ static double get(const uint32_t* w) { return __hiloint2double((int)w[1], (int)w[0]); }
 };
 
-// Load the record of `slot` from the block at `blk` and split it into corners + link.
-// Point-keyed leaves store one corner (lo == hi).
+// Load the record of `slot` from the block whose lane address (block + slot * 16) is
+// `blk` and split it into corners + link.  Record = lo corner, link, hi corner; point-keyed
+// leaves store the prefix "corner, link" only (lo == hi), so both kinds read the first rows
+// alike and only two-corner records fetch the rest.
 template <typename S, int D, int W, bool BOXKEY>
 __device__ __forceinline__ void load_entry(const unsigned char* __restrict__ blk, int slot, bool is_leaf,
                                            S (&lo)[D], S (&hi)[D], uint32_t& link)
 {
   constexpr int SW = ScalarWords<S>::N;
-  using Two = Record<2 * D * SW + 1, W>;
+  using Two = Record<2 * D * SW + SW, W>;
   using One = Record<D * SW + 1, W>;
   if (!BOXKEY && is_leaf)
   {
@@ -92,11 +97,19 @@ __device__ __forceinline__ void load_entry(const unsigned char* __restrict__ blk
 #pragma unroll
     for (int d = 0; d < D; ++d)
     {
-      lo[d] = ScalarWords<S>::get(w + 2 * d * SW);
-      hi[d] = ScalarWords<S>::get(w + (2 * d + 1) * SW);
+      lo[d] = ScalarWords<S>::get(w + d * SW);
+      hi[d] = ScalarWords<S>::get(w + (D + 1 + d) * SW);
     }
-    link = w[2 * D * SW];
+    link = w[D * SW];
   }
+}
+
+// Hide a pointer's provenance from the optimiser so it stays in one register pair (ptxas
+// otherwise re-adds the uniform base inside the traversal loop).
+__device__ __forceinline__ const unsigned char* opaque(const unsigned char* p)
+{
+  asm volatile("" : "+l"(p));
+  return p;
 }
 
 // ---- shared memory through 32-bit addresses (keeps the address math out of the loop) ----

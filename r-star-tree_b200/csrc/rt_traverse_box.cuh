@@ -55,11 +55,11 @@ box_traverse_kernel(const BoxLaunch p)
   const uint32_t stack = smem_addr(smem + warp * (stack_cap + HIT_BUF)); // 32-bit shared addresses
   const uint32_t hitbuf = stack + stack_cap * 4u;
 
-  const unsigned char* __restrict__ blocks = p.tree.blocks;
+  const unsigned char* lane_blocks = opaque(p.tree.blocks + slot * 16); // this lane's element of a row
   const uint32_t leaf_link_begin = p.tree.leaf_link_begin;
   const S* __restrict__ queries = static_cast<const S*>(p.queries);
 
-  unsigned long long visits_int = 0, visits_leaf = 0;
+  unsigned long long visits_int = 0, visits_leaf = 0, steps = 0;
   // stash slab owned by this warp (PASS_STASH)
   unsigned long long slab_pos = 0;
   uint32_t slab_left = 0;
@@ -105,36 +105,32 @@ box_traverse_kernel(const BoxLaunch p)
       {
         const uint32_t take = min(sp, (uint32_t)G);
         sp -= take;
+        // idle groups (fewer than G nodes left) mirror group 0: same addresses, so their
+        // loads coalesce into group 0's and nothing in the loop needs a branch
         const bool active = grp < take;
-        uint32_t node = RT_INVALID_ID;
-        if (active)
-          node = lds_u32(stack + (sp + grp) * 4u);
+        const uint32_t node = lds_u32(stack + (sp + (active ? grp : 0u)) * 4u);
         __syncwarp();
 
         const bool is_leaf = node >= leaf_link_begin;
-        uint32_t link = RT_INVALID_ID;
-        bool hit = false;
-        if (active)
-        {
-          S lo[D], hi[D];
-          load_entry<S, D, W, BOXKEY>(blocks + (unsigned long long)node * 16u, slot, is_leaf, lo, hi, link);
-          hit = link != RT_INVALID_ID;
+        uint32_t link;
+        S lo[D], hi[D];
+        load_entry<S, D, W, BOXKEY>(lane_blocks + (unsigned long long)node * 16u, slot, is_leaf, lo, hi, link);
+        bool hit = active && link != RT_INVALID_ID;
 #pragma unroll
-          for (int d = 0; d < D; ++d)
+        for (int d = 0; d < D; ++d)
+        {
+          if (BOXKEY && CONTAINS)
           {
-            if (BOXKEY && CONTAINS)
-            {
-              // leaf: key box inside the query box; internal: closed overlap
-              const S a = is_leaf ? lo[d] : hi[d];
-              const S b = is_leaf ? hi[d] : lo[d];
-              hit = hit && !(a < qlo[d]) && !(b > qhi[d]);
-            }
-            else
-            {
-              // closed overlap; for a point key (lo == hi) this IS the reference's
-              // is_inside: !(p < qmin) && !(p > qmax) per axis
-              hit = hit && !(hi[d] < qlo[d]) && !(lo[d] > qhi[d]);
-            }
+            // leaf: key box inside the query box; internal: closed overlap
+            const S a = is_leaf ? lo[d] : hi[d];
+            const S b = is_leaf ? hi[d] : lo[d];
+            hit = hit && !(a < qlo[d]) && !(b > qhi[d]);
+          }
+          else
+          {
+            // closed overlap; for a point key (lo == hi) this IS the reference's
+            // is_inside: !(p < qmin) && !(p > qmax) per axis
+            hit = hit && !(hi[d] < qlo[d]) && !(lo[d] > qhi[d]);
           }
         }
 
@@ -147,6 +143,7 @@ box_traverse_kernel(const BoxLaunch p)
           const uint32_t leaf_nodes = __popc(__ballot_sync(0xFFFFFFFFu, active && is_leaf && slot == 0));
           visits_leaf += leaf_nodes;
           visits_int += take - leaf_nodes;
+          ++steps;
         }
 
         // children to descend: compact onto the stack in lane order (keeps it level-sorted)
@@ -251,6 +248,7 @@ box_traverse_kernel(const BoxLaunch p)
   {
     atomicAdd(p.visit_stats + 0, visits_int);
     atomicAdd(p.visit_stats + 1, visits_leaf);
+    atomicAdd(p.visit_stats + 3, steps);
   }
 }
 

@@ -51,10 +51,10 @@ ray_traverse_kernel(const RayLaunch p)
   const uint32_t stack = smem_addr(smem + warp * (stack_cap + HIT_BUF));
   const uint32_t hitbuf = stack + stack_cap * 4u;
 
-  const unsigned char* __restrict__ blocks = p.tree.blocks;
+  const unsigned char* lane_blocks = opaque(p.tree.blocks + slot * 16); // this lane's element of a row
   const uint32_t leaf_link_begin = p.tree.leaf_link_begin;
 
-  unsigned long long visits_int = 0, visits_leaf = 0, rays_hit = 0;
+  unsigned long long visits_int = 0, visits_leaf = 0, rays_hit = 0, steps = 0;
 
   for (;;)
   {
@@ -101,35 +101,31 @@ ray_traverse_kernel(const RayLaunch p)
       {
         const uint32_t take = min(sp, (uint32_t)G);
         sp -= take;
+        // idle groups (fewer than G nodes left) mirror group 0: same addresses, so their
+        // loads coalesce into group 0's and nothing in the loop needs a branch
         const bool active = grp < take;
-        uint32_t node = RT_INVALID_ID;
-        if (active)
-          node = lds_u32(stack + (sp + grp) * 4u);
+        const uint32_t node = lds_u32(stack + (sp + (active ? grp : 0u)) * 4u);
         __syncwarp();
 
         const bool is_leaf = node >= leaf_link_begin;
-        uint32_t link = RT_INVALID_ID;
-        bool hit = false;
+        uint32_t link;
+        float lo[D], hi[D];
+        load_entry<float, D, W, BOXKEY>(lane_blocks + (unsigned long long)node * 16u, slot, is_leaf, lo, hi, link);
         float t0 = 0.0f;
-        if (active)
-        {
-          float lo[D], hi[D];
-          load_entry<float, D, W, BOXKEY>(blocks + (unsigned long long)node * 16u, slot, is_leaf, lo, hi, link);
-          float t1 = tmax;
+        float t1 = tmax;
 #pragma unroll
-          for (int d = 0; d < D; ++d)
-          {
-            const float a = __fmul_rn(__fsub_rn(lo[d], org[d]), inv[d]);
-            const float c = __fmul_rn(__fsub_rn(hi[d], org[d]), inv[d]);
-            const float tn = (c < a) ? c : a;
-            const float tf = (c < a) ? a : c;
-            t0 = (tn > t0) ? tn : t0;
-            t1 = (tf < t1) ? tf : t1;
-          }
-          hit = (link != RT_INVALID_ID) && (t0 <= t1);
-          if (RMODE == RAY_CLOSEST)
-            hit = hit && (is_leaf || t0 <= t_best);
+        for (int d = 0; d < D; ++d)
+        {
+          const float a = __fmul_rn(__fsub_rn(lo[d], org[d]), inv[d]);
+          const float c = __fmul_rn(__fsub_rn(hi[d], org[d]), inv[d]);
+          const float tn = (c < a) ? c : a;
+          const float tf = (c < a) ? a : c;
+          t0 = (tn > t0) ? tn : t0;
+          t1 = (tf < t1) ? tf : t1;
         }
+        bool hit = active && (link != RT_INVALID_ID) && (t0 <= t1);
+        if (RMODE == RAY_CLOSEST)
+          hit = hit && (is_leaf || t0 <= t_best);
 
         const uint32_t m_all = __ballot_sync(0xFFFFFFFFu, hit);
         const uint32_t m_leaf = __ballot_sync(0xFFFFFFFFu, hit && is_leaf);
@@ -140,6 +136,7 @@ ray_traverse_kernel(const RayLaunch p)
           const uint32_t leaf_nodes = __popc(__ballot_sync(0xFFFFFFFFu, active && is_leaf && slot == 0));
           visits_leaf += leaf_nodes;
           visits_int += take - leaf_nodes;
+          ++steps;
         }
 
         if (hit && !is_leaf)
@@ -233,6 +230,7 @@ ray_traverse_kernel(const RayLaunch p)
   {
     atomicAdd(p.visit_stats + 0, visits_int);
     atomicAdd(p.visit_stats + 1, visits_leaf);
+    atomicAdd(p.visit_stats + 3, steps);
   }
   if ((RMODE == RAY_CLOSEST || RMODE == RAY_ANY) && lane == 0 && rays_hit != 0)
     atomicAdd(p.visit_stats + 2, rays_hit);

@@ -9,7 +9,7 @@
 //   * nodes renumbered breadth-first, so a level is one contiguous range, siblings
 //     are adjacent and the top of the tree is a small prefix of the buffer;
 //   * one fixed-width block per node, W = MAX_ENTRIES rounded up to 8 or 16 slots; a
-//     slot's record is  lo_0 hi_0 ... lo_{D-1} hi_{D-1} link  (32-bit words), stored as a
+//     slot's record is  lo_0 .. lo_{D-1} link hi_0 .. hi_{D-1}  (32-bit words), stored as a
 //     structure of arrays of 16-byte vectors: row k holds words 4k..4k+3 of all W slots,
 //     so a warp lane reads "its" child with one coalesced 128-bit load per row;
 //   * leaves of point-keyed trees keep one corner only:  p_0 .. p_{D-1} id;
@@ -300,15 +300,10 @@ device_tree_t flatten_device(FlattenResult const& flat, id_source ids = id_sourc
           lo = gtraits::min_point(g, static_cast<int>(d));
           hi = gtraits::max_point(g, static_cast<int>(d));
         }
-        if (one_corner)
-        {
-          put_scalar(block, words, c, d * SW, lo);
-        }
-        else
-        {
-          put_scalar(block, words, c, 2 * d * SW, lo);
-          put_scalar(block, words, c, (2 * d + 1) * SW, hi);
-        }
+        // record: lo corner, link (one word, plus an alignment word for 64-bit scalars), hi corner
+        put_scalar(block, words, c, d * SW, lo);
+        if (!one_corner)
+          put_scalar(block, words, c, (D + 1 + d) * SW, hi);
       }
       if (used)
       {
@@ -326,7 +321,7 @@ device_tree_t flatten_device(FlattenResult const& flat, id_source ids = id_sourc
           link = static_cast<std::uint32_t>(child_offset / 16);
         }
       }
-      *word_at(block, words, c, words - 1) = link;
+      *word_at(block, words, c, D * SW) = link;
     }
   }
   return out;

@@ -6,7 +6,8 @@ TAIL_BYTES = (0, 4, 8, 16)
 
 
 def record_words(dim, scalar_bytes, two_corners):
-    return (2 if two_corners else 1) * dim * (scalar_bytes // 4) + 1
+    sw = scalar_bytes // 4
+    return 2 * dim * sw + sw if two_corners else dim * sw + 1
 
 
 def block_bytes(width, words):
@@ -47,13 +48,14 @@ def decode_image(image, capi):
         one_corner = is_leaf and d.key_kind == capi.RT_KEY_POINT
         words = record_words(D, sb, not one_corner)
         rec = block_records(raw, start, W, words)
-        link = rec[:, words - 1]
+        sw = sb // 4
+        link = rec[:, D * sw]                          # record: lo corner, link (+pad), hi corner
         valid = link != capi.RT_INVALID_ID
-        scalars = np.ascontiguousarray(rec[:, :words - 1]).view(dt)   # [W][corners*D]
+        lo = np.ascontiguousarray(rec[:, :D * sw]).view(dt)[valid]
         if one_corner:
-            lo = hi = scalars[valid]
+            hi = lo
         else:
-            lo, hi = scalars[valid][:, 0::2], scalars[valid][:, 1::2]
+            hi = np.ascontiguousarray(rec[:, (D + 1) * sw:(2 * D + 1) * sw]).view(dt)[valid]
         out.append((is_leaf, lo, hi, link[valid], valid))
     return out
 
