@@ -33,12 +33,16 @@
 
 #include <rtree_b200.h>
 
-#include "geometry.hpp"
-
 namespace eh
 {
 namespace rtree
 {
+
+// Only the customisation point is needed (min_point / max_point / DIM / scalar_type), and only
+// by declaration, so this header works with this library's RTree/geometry.hpp AND with the
+// reference's own RTree/geometry_traits.hpp.
+template <typename GeometryType>
+struct geometry_traits;
 
 /// what a leaf slot reports as the "id" of a hit
 enum class id_source

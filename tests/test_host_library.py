@@ -164,3 +164,56 @@ def test_empty_tree_image(rtb):
     assert d.num_nodes == 1 and d.leaf_level == 0 and d.num_values == 0
     (is_leaf, lo, hi, link, valid), = decode_image(image, rtb.capi)
     assert is_leaf and link.size == 0 and not valid.any()
+
+
+REF_INCLUDE = "/root/reference/include"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF_INCLUDE), reason="reference sources not present")
+def test_device_layout_compiles_against_reference_headers(rtb, tmp_path):
+    """the reference's RTree + our device_layout.hpp, nothing else of
+    ours, produce the same image as our host library."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "with_reference.cpp"
+    src.write_text(r'''
+#include <RTree.hpp>                  // the REFERENCE's umbrella header
+#include <RTree/device_layout.hpp>    // ours
+#include <cstdio>
+#include <random>
+int main()
+{
+  using point = eh::rtree::point_t<float, 3>;
+  using box = eh::rtree::aabb_t<point>;
+  using tree_t = eh::rtree::RTree<box, point, unsigned>;
+  tree_t tree;
+  std::mt19937 rng(5);
+  std::uniform_real_distribution<float> u(0.f, 1.f);
+  for (unsigned i = 0; i < 5000; ++i)
+  {
+    float x = u(rng), y = u(rng), z = u(rng);
+    tree.insert({ point(x, y, z), i });
+    std::printf("%a %a %a\n", x, y, z);
+  }
+  auto image = eh::rtree::flatten_device<tree_t::MAX_ENTRIES, false>(tree.flatten(), eh::rtree::id_source::mapped_value);
+  rt_tree_desc d = image.desc();
+  unsigned long long h = 1469598103934665603ull;
+  for (unsigned long long i = 0; i < d.blocks_bytes; ++i) h = (h ^ image.blocks.data()[i]) * 1099511628211ull;
+  std::fprintf(stderr, "%u %u %llu %llu\n", d.num_nodes, d.leaf_level, (unsigned long long)d.blocks_bytes, h);
+  return 0;
+}
+''')
+    exe = tmp_path / "with_reference"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", REF_INCLUDE, "-I",
+                    os.path.join(root, "r-star-tree_b200", "include"), "-I", os.path.join(root, "include"),
+                    "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True)
+    pts = np.array([[float.fromhex(v) for v in line.split()] for line in out.stdout.split("\n") if line], np.float32)
+    num_nodes, leaf_level, nbytes, fnv = [int(v) for v in out.stderr.split()]
+    image = rtb.RTree(4).insert(pts).flatten_device(ids_from_mapped=True)
+    assert (image.desc.num_nodes, image.desc.leaf_level, image.desc.blocks_bytes) == (num_nodes, leaf_level, nbytes)
+    h = 1469598103934665603
+    for byte in image.blocks().tobytes():
+        h = ((h ^ byte) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    assert h == fnv
