@@ -11,7 +11,8 @@ CPU by the host library's insert / RStarSplit / reinsert) searched by 16 M small
            CUDA events on the launching stream, barrier + synchronize on both sides, max
            over ranks.  Inputs (384 MB of queries + 429 MB of tree) exceed the 126 MB L2.
   e2e      the same metric through the C ABI with HOST buffers: pinned queries in, pinned
-           offsets + ids out, both copies inside the timed region.
+           offsets + ids out, both copies inside the timed region (the engine cuts such a call
+           into batches and overlaps their copies with the traversal of their neighbours).
   roofline algorithmic bytes per launch (SURVEY.md 8d formula on the node-visit totals the
            engine counts with RT_COLLECT_VISITS) / average duration of the traversal kernel
            (CUDA events inside the timed steps), against MEASURED_PEAKS.json's HBM number.
@@ -389,6 +390,9 @@ def main():
             "e2e": {"value": total_q * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
                     "ms_per_step": e2e_ms / args.steps,
+                    "batches": int(e2e_stats["batches"]),
+                    "note": "pipelined: the call is cut into batches whose H2D / traversal / D2H overlap; "
+                            "breakdown_ms are per-phase SUMS over the batches (they overlap one another)",
                     "breakdown_ms": {k: round(e2e_stats[k], 3) for k in
                                      ("h2d_ms", "reorder_ms", "traverse_ms", "finish_ms", "d2h_ms")}},
             "gpu_launches": int(launches_all),

@@ -172,7 +172,8 @@ typedef struct rt_ray_result
 
 /* Timings of the LAST query call on the handle (CUDA events on the handle's stream)
  * and, with RT_COLLECT_VISITS, the node-visit totals that define the algorithmic
- * bytes of the batch.                                                                 */
+ * bytes of the batch.  total_ms is the whole call; the per-phase times are sums over the
+ * batches of the call, which overlap one another when the call was pipelined.          */
 typedef struct rt_stats
 {
   float total_ms;    /* first H2D to last D2H */
@@ -187,6 +188,8 @@ typedef struct rt_stats
   uint64_t visits_leaf;
   uint64_t algorithmic_bytes; /* SURVEY.md 8d formula on the visit totals */
   uint64_t traverse_steps;    /* warp loop iterations; visits / (steps * 32/W) = lane-group use */
+  uint32_t batches;           /* batches the call was cut into (> 1: pipelined, see RT_OPT_PIPELINE_BATCH) */
+  uint32_t reserved;
 } rt_stats;
 
 /* Copy the tree image to `device` (cudaSetDevice(device) is called by every entry
@@ -209,6 +212,24 @@ void rt_free(rt_tree* tree);
 /* Launch on this CUDA stream (a cudaStream_t) instead of the handle's own.          */
 int rt_set_stream(rt_tree* tree, void* cuda_stream);
 int rt_get_stats(const rt_tree* tree, rt_stats* out);
+/* Tuning knobs.
+ * RT_OPT_PIPELINE_BATCH: a query call with a HOST result and at least two batches' worth of
+ *   queries is cut into batches of about this many queries; the copies of neighbouring batches
+ *   (H2D of the next, D2H of the previous) run under the traversal of the current one.  The
+ *   result is the same CSR as an unpipelined call.  0 = never pipeline.  Default 2 Mi
+ *   (environment override at rt_upload: RTB_PIPELINE_BATCH).                              */
+#define RT_OPT_PIPELINE_BATCH 1u
+/* RT_OPT_QUERY_CHUNK: queries a warp claims at a time (default 4).
+ * RT_OPT_WORK_RANGES: 0 (default) = the queries of a launch are cut into one contiguous range per
+ *   SM, the warps of an SM working through "their" range first and stealing from the others
+ *   afterwards; N > 0 = N ranges, CTA b starting on range b mod N (1 = a single global cursor).
+ *   Neither changes any result.                                                            */
+#define RT_OPT_QUERY_CHUNK 2u
+#define RT_OPT_WORK_RANGES 3u
+/* RT_OPT_TRAVERSE_GRID: CTAs of the persistent traversal kernels; 0 (default) = as many as are
+ *   resident at once (SMs x occupancy; one CTA slot per SM is left free in pipelined calls).    */
+#define RT_OPT_TRAVERSE_GRID 4u
+int rt_set_option(rt_tree* tree, uint32_t option, uint64_t value);
 /* Device copy of the blocks, e.g. to broadcast the tree to peer GPUs.               */
 int rt_tree_device_blocks(const rt_tree* tree, void** device_ptr, uint64_t* bytes);
 int rt_tree_get_desc(const rt_tree* tree, rt_tree_desc* out);

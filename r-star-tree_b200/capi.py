@@ -23,12 +23,13 @@ RT_RAY_ALL_HITS, RT_RAY_CLOSEST, RT_RAY_ANY = 0, 1, 2
 RT_QUERIES_ON_DEVICE, RT_RESULT_ON_DEVICE, RT_UNSORTED = 0x1, 0x2, 0x4
 RT_COUNT_ONLY, RT_COLLECT_VISITS, RT_NO_REORDER = 0x8, 0x10, 0x20
 RT_INVALID_ID = 0xFFFFFFFF
+RT_OPT_PIPELINE_BATCH, RT_OPT_QUERY_CHUNK, RT_OPT_WORK_RANGES, RT_OPT_TRAVERSE_GRID = 1, 2, 3, 4
 
 SCALAR_DTYPES = {RT_F32: np.float32, RT_F64: np.float64, RT_I32: np.int32}
 
 # every symbol include/rtree_b200.h declares
 EXPORTS = ["rt_upload", "rt_query_boxes", "rt_query_rays", "rt_free", "rt_set_stream",
-           "rt_get_stats", "rt_tree_device_blocks", "rt_tree_get_desc", "rt_last_error",
+           "rt_set_option", "rt_get_stats", "rt_tree_device_blocks", "rt_tree_get_desc", "rt_last_error",
            "rt_abi_version", "rt_device_count"]
 
 
@@ -65,7 +66,8 @@ class RtStats(C.Structure):
                 ("traverse_ms", C.c_float), ("finish_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("kernel_launches", C.c_uint32), ("deferred_queries", C.c_uint32),
                 ("visits_internal", C.c_uint64), ("visits_leaf", C.c_uint64),
-                ("algorithmic_bytes", C.c_uint64), ("traverse_steps", C.c_uint64)]
+                ("algorithmic_bytes", C.c_uint64), ("traverse_steps", C.c_uint64),
+                ("batches", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -98,6 +100,8 @@ def lib():
         L.rt_free.argtypes = [C.c_void_p]
         L.rt_set_stream.restype = C.c_int
         L.rt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.rt_set_option.restype = C.c_int
+        L.rt_set_option.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
         L.rt_get_stats.restype = C.c_int
         L.rt_get_stats.argtypes = [C.c_void_p, C.POINTER(RtStats)]
         L.rt_tree_device_blocks.restype = C.c_int
@@ -169,6 +173,9 @@ class DeviceTree:
 
     def set_stream(self, cuda_stream):
         _check(lib().rt_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def set_option(self, option, value):
+        _check(lib().rt_set_option(self._h, C.c_uint32(option), C.c_uint64(int(value))))
 
     def stats(self):
         s = RtStats()

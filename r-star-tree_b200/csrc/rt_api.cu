@@ -1,13 +1,17 @@
 // rt_api.cu -- the C ABI of include/rtree_b200.h: device buffers, streams, events and the
 // per-call pipeline around the traversal kernels.  No query-path arithmetic lives here.
 //
-// rt_query_boxes pipeline (default flags), all on the handle's stream:
+// rt_query_boxes pipeline (default flags), per batch of queries:
 //   H2D queries -> reorder (Morton cells) -> traversal PASS_STASH (counts + sorted short
-//   lists into the stash) -> scan (CSR offsets) -> [8-byte D2H: total, #deferred] ->
+//   lists into the stash) -> scan (CSR offsets) -> [64-byte D2H: total, #deferred] ->
 //   gather stash -> PASS_WRITE over the deferred queries only -> sort their long lists ->
 //   D2H offsets + ids.
 // With RT_COLLECT_VISITS / RT_COUNT_ONLY the plain two-pass form (PASS_COUNT[_STATS],
 // scan, PASS_WRITE over all queries) runs instead.
+// A call whose result stays on the device is ONE batch on the handle's stream.  A large call
+// with a host result is cut into batches that rotate through NSLOT working sets on their own
+// streams (forked from / joined to the handle's stream), so the PCIe copies of neighbouring
+// batches run under the traversal of the current one.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -112,10 +116,10 @@ struct HostBuf
   }
 };
 
-// device-side counters of one call (one 64-byte block, zeroed per call)
+// device-side counters of one batch (one 64-byte block, zeroed per batch)
 struct Counters
 {
-  unsigned long long work;        // query chunk cursor
+  unsigned long long unused;
   unsigned long long stash_cursor;
   unsigned long long visits[4];   // internal visits, leaf visits, rays with a hit, loop steps
   unsigned long long total;       // filled by copying offsets[n]
@@ -131,9 +135,44 @@ enum
   EV_H2D,
   EV_REORDER,
   EV_TRAVERSE,
+  EV_COUNTED, // scan done, counters on their way to the host
+  EV_WRITE,   // phase 2 begins
   EV_FINISH,
   EV_D2H,
   EV_COUNT
+};
+
+constexpr int NSLOT = 3;
+constexpr uint64_t DEFAULT_PIPELINE_BATCH = 2u << 20; // queries per batch of a pipelined call
+
+// The working set of one batch of queries.  A call that leaves its result on the device, or a
+// small one, is a single batch on slot 0 and the caller's stream.  A large call with a host
+// result is cut into batches that rotate through the slots, each slot on its own stream, so
+// that the H2D copy of batch k+1 and the D2H copy of batch k-1 run under the traversal of
+// batch k (PCIe is full duplex and both copy engines are otherwise idle).
+struct Slot
+{
+  DevBuf d_queries, d_order, d_counts, d_offsets, d_ids, d_stash, d_stash_pos, d_deferred, d_big, d_scratch,
+      d_counters, d_cursors;
+  HostBuf h_counters;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  unsigned long long stash_wanted = 0; // pool size the last batch on this slot would have needed
+
+  void release()
+  {
+    DevBuf* dev[] = { &d_queries, &d_order, &d_counts, &d_offsets, &d_ids, &d_stash,
+                      &d_stash_pos, &d_deferred, &d_big, &d_scratch, &d_counters, &d_cursors };
+    for (DevBuf* b : dev)
+      b->release();
+    h_counters.release();
+    if (done)
+      cudaEventDestroy(done);
+    if (stream)
+      cudaStreamDestroy(stream);
+    done = nullptr;
+    stream = nullptr;
+  }
 };
 } // namespace
 
@@ -146,14 +185,16 @@ struct rt_tree
   unsigned char* d_blocks = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[EV_COUNT] = {};
-  // extra events bracketing the second traversal
-  cudaEvent_t ev_t2_begin = nullptr, ev_t2_end = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<cudaEvent_t> events; // EV_COUNT per batch of a call, grow-only
 
-  DevBuf d_queries, d_order, d_counts, d_offsets, d_ids, d_stash, d_stash_pos, d_deferred, d_big,
-      d_scratch, d_counters, d_ray_t, d_ray_id, d_ray_any;
-  HostBuf h_counters, h_offsets, h_ids, h_ray_t, h_ray_id, h_ray_any;
-  unsigned long long stash_wanted = 0; // pool size the last call would have needed
+  Slot slot[NSLOT];
+  DevBuf d_ray_t, d_ray_id, d_ray_any;
+  HostBuf h_offsets, h_ids, h_ray_t, h_ray_id, h_ray_any;
+  uint64_t pipeline_batch = DEFAULT_PIPELINE_BATCH;
+  uint32_t query_chunk = 0, work_ranges = 0; // 0 = the kernels' defaults
+  int traverse_grid = 0;                     // 0 = fill the GPU
+  unsigned long long ids_wanted = 0; // hit total of the last pipelined call (sizes h_ids up front)
   rt_stats stats;
 };
 
@@ -221,6 +262,20 @@ float elapsed(cudaEvent_t a, cudaEvent_t b)
   return ms;
 }
 
+// the EV_COUNT events of batch `index` of the running call
+int batch_events(rt_tree* t, size_t index, cudaEvent_t** out)
+{
+  const size_t need = (index + 1) * EV_COUNT;
+  while (t->events.size() < need)
+  {
+    cudaEvent_t e = nullptr;
+    RT_CUDA(cudaEventCreate(&e));
+    t->events.push_back(e);
+  }
+  *out = t->events.data() + index * EV_COUNT;
+  return RT_OK;
+}
+
 uint64_t algorithmic_bytes_boxes(const rt_tree* t, uint64_t n, uint64_t total, uint64_t v_int, uint64_t v_leaf)
 {
   // V_int*B_int + V_leaf*B_leaf + query bytes + 8 (CSR offset) + 4*hits
@@ -229,6 +284,247 @@ uint64_t algorithmic_bytes_boxes(const rt_tree* t, uint64_t n, uint64_t total, u
   const uint64_t b_int = M * (2 * D * s + 4);
   const uint64_t b_leaf = t->desc.key_kind == RT_KEY_BOX ? b_int : M * (D * s + 4);
   return v_int * b_int + v_leaf * b_leaf + n * (2 * D * s + 8) + 4 * total;
+}
+
+// ---- one rt_query_boxes call = one or more batches, each issued in two phases ----------------
+struct BoxCall
+{
+  rtb::box_launch_fn launch;
+  size_t query_stride; // bytes per query
+  bool on_device, keep_on_device, count_only, collect, sorted, reorder, two_pass, pipelined;
+};
+
+struct Batch
+{
+  Slot* slot = nullptr;
+  cudaStream_t st = nullptr;
+  cudaEvent_t* ev = nullptr;
+  const void* queries = nullptr; // this batch's queries, host or device memory
+  uint64_t first = 0, n = 0;
+  rtb::BoxLaunch L;
+  const uint32_t* d_order = nullptr;
+  Counters hc;
+  uint32_t launches = 0, deferred = 0;
+};
+
+// phase 1: H2D -> reorder -> first traversal -> scan -> counters on their way to the host
+int box_issue_count(rt_tree* t, const BoxCall& c, Batch& b)
+{
+  Slot& s = *b.slot;
+  const uint64_t n = b.n;
+  cudaStream_t st = b.st;
+  const bool reorder = c.reorder && n >= 4096;
+
+  RT_CUDA(s.d_counters.reserve(sizeof(Counters)));
+  RT_CUDA(s.d_cursors.reserve(rtb::MAX_WORK_RANGES * sizeof(unsigned int)));
+  RT_CUDA(s.h_counters.reserve(sizeof(Counters)));
+  RT_CUDA(s.d_counts.reserve((size_t)(n + 4) * sizeof(uint32_t)));
+  RT_CUDA(s.d_offsets.reserve((size_t)(n + 1) * sizeof(unsigned long long)));
+  size_t scratch = rtb::scan_scratch_bytes(n);
+  if (reorder)
+    scratch = scratch > rtb::reorder_scratch_bytes(n) ? scratch : rtb::reorder_scratch_bytes(n);
+  RT_CUDA(s.d_scratch.reserve(scratch));
+  RT_CUDA(s.d_big.reserve((size_t)(n + 1) * sizeof(uint32_t)));
+  const size_t query_bytes = (size_t)n * c.query_stride;
+  if (!c.on_device)
+    RT_CUDA(s.d_queries.reserve(query_bytes ? query_bytes : 16));
+  if (reorder)
+    RT_CUDA(s.d_order.reserve((size_t)n * sizeof(uint32_t)));
+  unsigned long long stash_capacity = 0;
+  if (!c.two_pass)
+  {
+    RT_CUDA(s.d_stash_pos.reserve((size_t)(n + 1) * sizeof(uint32_t)));
+    RT_CUDA(s.d_deferred.reserve((size_t)(n + 1) * sizeof(uint32_t)));
+    // pool: what the previous batch needed (+25%), else ~12 ids per query; never more than a
+    // quarter of the free memory, never more than 32-bit positions can address
+    unsigned long long want = s.stash_wanted ? s.stash_wanted + s.stash_wanted / 4 : n * 12ull;
+    want += 4ull * rtb::STASH_SLAB * 1024;
+    if (want > 0xFFFFF000ull)
+      want = 0xFFFFF000ull;
+    const unsigned long long have = s.d_stash.cap / sizeof(uint32_t);
+    if (want > have)
+    {
+      // growing: cap the pool at a quarter of the free memory (cudaMemGetInfo costs
+      // milliseconds, so it is only asked when the pool really has to grow)
+      size_t free_b = 0, total_b = 0;
+      RT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      const unsigned long long limit = (unsigned long long)(free_b / 4 / sizeof(uint32_t)) + have;
+      if (want > limit)
+        want = limit;
+    }
+    if (want > have)
+    {
+      cudaError_t e = s.d_stash.reserve((size_t)want * sizeof(uint32_t));
+      if (e != cudaSuccess)
+        cudaGetLastError(); // keep whatever we have; overflowing queries are deferred
+    }
+    stash_capacity = s.d_stash.cap / sizeof(uint32_t);
+    if (stash_capacity > 0xFFFFF000ull)
+      stash_capacity = 0xFFFFF000ull;
+    // test knob: pretend the pool is this small so the exhaustion path can be exercised
+    if (const char* limit = std::getenv("RTB_STASH_LIMIT_IDS"))
+    {
+      const unsigned long long cap = std::strtoull(limit, nullptr, 10);
+      if (cap < stash_capacity)
+        stash_capacity = cap;
+    }
+  }
+
+  // ---- H2D ---------------------------------------------------------------------------
+  RT_CUDA(cudaEventRecord(b.ev[EV_BEGIN], st));
+  const void* d_q = b.queries;
+  if (!c.on_device)
+  {
+    if (query_bytes)
+      RT_CUDA(cudaMemcpyAsync(s.d_queries.p, b.queries, query_bytes, cudaMemcpyHostToDevice, st));
+    d_q = s.d_queries.p;
+  }
+  RT_CUDA(cudaMemsetAsync(s.d_counters.p, 0, sizeof(Counters), st));
+  RT_CUDA(cudaEventRecord(b.ev[EV_H2D], st));
+
+  // ---- coherence pass ----------------------------------------------------------------
+  b.d_order = nullptr;
+  if (reorder)
+  {
+    RT_CUDA(rtb::launch_reorder(d_q, t->desc.scalar, t->desc.dim, 2 * t->desc.dim, n, s.d_order.as<uint32_t>(),
+                                s.d_scratch.p, st, &b.launches));
+    b.d_order = s.d_order.as<uint32_t>();
+  }
+  RT_CUDA(cudaEventRecord(b.ev[EV_REORDER], st));
+
+  // ---- first traversal -----------------------------------------------------------------
+  Counters* dc = s.d_counters.as<Counters>();
+  rtb::BoxLaunch& L = b.L;
+  std::memset(&L, 0, sizeof L);
+  L.tree = t->dev;
+  L.queries = d_q;
+  L.order = b.d_order;
+  L.n = n;
+  L.counts = s.d_counts.as<uint32_t>();
+  L.offsets = s.d_offsets.as<unsigned long long>();
+  L.stash = s.d_stash.as<uint32_t>();
+  L.stash_pos = s.d_stash_pos.as<uint32_t>();
+  L.stash_capacity = stash_capacity;
+  L.stash_cursor = &dc->stash_cursor;
+  L.deferred_list = s.d_deferred.as<uint32_t>();
+  L.deferred_count = &dc->deferred;
+  L.big_list = s.d_big.as<uint32_t>();
+  L.big_count = &dc->big;
+  L.work.cursors = s.d_cursors.as<unsigned int>();
+  L.work.chunk = t->query_chunk;
+  L.work.ranges = t->work_ranges;
+  L.grid = t->traverse_grid ? t->traverse_grid : (c.pipelined ? -1 : 0);
+  L.visit_stats = dc->visits;
+  L.sorted = c.sorted ? 1u : 0u;
+  L.stream = st;
+  L.pass = c.two_pass ? (c.collect ? rtb::PASS_COUNT_STATS : rtb::PASS_COUNT) : rtb::PASS_STASH;
+  if (n > 0)
+  {
+    RT_CUDA(c.launch(L));
+    ++b.launches;
+  }
+  RT_CUDA(cudaEventRecord(b.ev[EV_TRAVERSE], st));
+
+  // ---- CSR offsets, then the 64-byte read-back that sizes the id buffer -----------------
+  RT_CUDA(rtb::launch_exclusive_scan(s.d_counts.as<uint32_t>(), n, s.d_offsets.as<unsigned long long>(),
+                                     s.d_scratch.p, st, &b.launches));
+  RT_CUDA(cudaMemcpyAsync(&dc->total, s.d_offsets.as<unsigned long long>() + n, sizeof(unsigned long long),
+                          cudaMemcpyDeviceToDevice, st));
+  RT_CUDA(cudaMemcpyAsync(s.h_counters.p, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaEventRecord(b.ev[EV_COUNTED], st));
+  return RT_OK;
+}
+
+// between the phases: wait for the batch's counters
+int box_wait_counted(Batch& b)
+{
+  RT_CUDA(cudaEventSynchronize(b.ev[EV_COUNTED]));
+  b.hc = *b.slot->h_counters.as<Counters>();
+  return RT_OK;
+}
+
+// phase 2: gather the stash -> second traversal of the deferred queries -> sort long lists ->
+// D2H.  `base` = hits of the batches before this one; a host result goes to
+// h_offsets[first ..] (rebased) and h_ids[base ..].
+int box_issue_write(rt_tree* t, const BoxCall& c, Batch& b, unsigned long long base, bool last_batch)
+{
+  Slot& s = *b.slot;
+  const uint64_t n = b.n;
+  cudaStream_t st = b.st;
+  Counters* dc = s.d_counters.as<Counters>();
+  const unsigned long long total = b.hc.total;
+  if (!c.two_pass)
+    s.stash_wanted = b.hc.stash_cursor;
+  rtb::BoxLaunch& L = b.L;
+
+  RT_CUDA(cudaEventRecord(b.ev[EV_WRITE], st));
+  if (!c.count_only)
+  {
+    RT_CUDA(s.d_ids.reserve((size_t)(total ? total : 1) * sizeof(uint32_t)));
+    bool second = false;
+    if (c.two_pass)
+    {
+      second = n > 0 && total > 0;
+      L.order = b.d_order;
+      L.n = n;
+      b.deferred = (uint32_t)n;
+    }
+    else
+    {
+      RT_CUDA(rtb::launch_gather_stash(s.d_stash.as<uint32_t>(), s.d_stash_pos.as<uint32_t>(),
+                                       s.d_offsets.as<unsigned long long>(), n, s.d_ids.as<uint32_t>(), st,
+                                       &b.launches));
+      b.deferred = b.hc.deferred;
+      second = b.deferred > 0;
+      L.order = s.d_deferred.as<uint32_t>();
+      L.n = b.deferred;
+    }
+    if (second)
+    {
+      L.pass = rtb::PASS_WRITE;
+      L.ids = s.d_ids.as<uint32_t>();
+      RT_CUDA(c.launch(L));
+      ++b.launches;
+      if (c.sorted)
+        RT_CUDA(rtb::launch_sort_segments(s.d_big.as<uint32_t>(), &dc->big, (uint32_t)L.n,
+                                          s.d_offsets.as<unsigned long long>(), s.d_ids.as<uint32_t>(), st,
+                                          &b.launches));
+    }
+  }
+  RT_CUDA(cudaEventRecord(b.ev[EV_FINISH], st));
+
+  if (!c.keep_on_device)
+  {
+    if (base)
+      RT_CUDA(rtb::launch_add_base(s.d_offsets.as<unsigned long long>(), n + 1, base, st, &b.launches));
+    const size_t n_off = (size_t)n + (last_batch ? 1 : 0);
+    if (n_off)
+      RT_CUDA(cudaMemcpyAsync(t->h_offsets.as<unsigned long long>() + b.first, s.d_offsets.p,
+                              n_off * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (!c.count_only && total)
+      RT_CUDA(cudaMemcpyAsync(t->h_ids.as<uint32_t>() + base, s.d_ids.p, (size_t)total * sizeof(uint32_t),
+                              cudaMemcpyDeviceToHost, st));
+  }
+  RT_CUDA(cudaEventRecord(b.ev[EV_D2H], st));
+  return RT_OK;
+}
+
+// Make the pinned id buffer hold `need` ids, keeping the first `keep` (copies into it may be in
+// flight on the slot streams).  `hint` is the expected final size.
+int grow_host_ids(rt_tree* t, unsigned long long need, unsigned long long keep, unsigned long long hint)
+{
+  if ((size_t)need * sizeof(uint32_t) <= t->h_ids.cap)
+    return RT_OK;
+  for (Slot& s : t->slot)
+    RT_CUDA(cudaStreamSynchronize(s.stream));
+  HostBuf bigger;
+  const unsigned long long want = need > hint ? need : hint;
+  RT_CUDA(bigger.reserve((size_t)want * sizeof(uint32_t)));
+  if (keep)
+    std::memcpy(bigger.p, t->h_ids.p, (size_t)keep * sizeof(uint32_t));
+  t->h_ids.release();
+  t->h_ids = bigger;
+  return RT_OK;
 }
 } // namespace
 
@@ -269,6 +565,8 @@ int rt_upload(const rt_tree_desc* desc, int device, rt_tree** out)
   t->levels.assign(desc->level_node_begin, desc->level_node_begin + desc->num_levels + 1);
   t->desc.level_node_begin = t->levels.data();
   std::memset(&t->stats, 0, sizeof t->stats);
+  if (const char* batch = std::getenv("RTB_PIPELINE_BATCH"))
+    t->pipeline_batch = std::strtoull(batch, nullptr, 10);
 
   auto cleanup = [&](int code, const std::string& what)
   {
@@ -282,12 +580,13 @@ int rt_upload(const rt_tree_desc* desc, int device, rt_tree** out)
   if (e != cudaSuccess)
     return cleanup(RT_E_CUDA, std::string("rt_upload: stream: ") + cudaGetErrorString(e));
   t->stream = t->own_stream;
-  for (int i = 0; i < EV_COUNT; ++i)
+  for (Slot& s : t->slot)
   {
-    if ((e = cudaEventCreate(&t->ev[i])) != cudaSuccess)
-      return cleanup(RT_E_CUDA, std::string("rt_upload: event: ") + cudaGetErrorString(e));
+    if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess
+        || (e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess)
+      return cleanup(RT_E_CUDA, std::string("rt_upload: slot stream: ") + cudaGetErrorString(e));
   }
-  if ((e = cudaEventCreate(&t->ev_t2_begin)) != cudaSuccess || (e = cudaEventCreate(&t->ev_t2_end)) != cudaSuccess)
+  if ((e = cudaEventCreate(&t->ev_fork)) != cudaSuccess || (e = cudaEventCreate(&t->ev_join)) != cudaSuccess)
     return cleanup(RT_E_CUDA, std::string("rt_upload: event: ") + cudaGetErrorString(e));
   e = cudaMemcpyAsync(t->d_blocks, desc->blocks, desc->blocks_bytes,
                       desc->blocks_memory == RT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
@@ -296,9 +595,6 @@ int rt_upload(const rt_tree_desc* desc, int device, rt_tree** out)
     e = cudaStreamSynchronize(t->stream);
   if (e != cudaSuccess)
     return cleanup(RT_E_CUDA, std::string("rt_upload: copy of blocks: ") + cudaGetErrorString(e));
-  if ((e = t->d_counters.reserve(sizeof(Counters))) != cudaSuccess
-      || (e = t->h_counters.reserve(sizeof(Counters))) != cudaSuccess)
-    return cleanup(RT_E_NOMEM, std::string("rt_upload: counters: ") + cudaGetErrorString(e));
 
   t->desc.blocks = t->d_blocks;
   t->desc.blocks_memory = RT_MEM_DEVICE;
@@ -317,23 +613,26 @@ void rt_free(rt_tree* t)
   cudaSetDevice(t->device);
   if (t->own_stream)
     cudaStreamSynchronize(t->own_stream);
-  DevBuf* dev[] = { &t->d_queries, &t->d_order, &t->d_counts, &t->d_offsets, &t->d_ids, &t->d_stash,
-                    &t->d_stash_pos, &t->d_deferred, &t->d_big, &t->d_scratch, &t->d_counters,
-                    &t->d_ray_t, &t->d_ray_id, &t->d_ray_any };
+  for (Slot& s : t->slot)
+  {
+    if (s.stream)
+      cudaStreamSynchronize(s.stream);
+    s.release();
+  }
+  DevBuf* dev[] = { &t->d_ray_t, &t->d_ray_id, &t->d_ray_any };
   for (DevBuf* b : dev)
     b->release();
-  HostBuf* host[] = { &t->h_counters, &t->h_offsets, &t->h_ids, &t->h_ray_t, &t->h_ray_id, &t->h_ray_any };
+  HostBuf* host[] = { &t->h_offsets, &t->h_ids, &t->h_ray_t, &t->h_ray_id, &t->h_ray_any };
   for (HostBuf* b : host)
     b->release();
   if (t->d_blocks)
     cudaFree(t->d_blocks);
-  for (int i = 0; i < EV_COUNT; ++i)
-    if (t->ev[i])
-      cudaEventDestroy(t->ev[i]);
-  if (t->ev_t2_begin)
-    cudaEventDestroy(t->ev_t2_begin);
-  if (t->ev_t2_end)
-    cudaEventDestroy(t->ev_t2_end);
+  for (cudaEvent_t e : t->events)
+    cudaEventDestroy(e);
+  if (t->ev_fork)
+    cudaEventDestroy(t->ev_fork);
+  if (t->ev_join)
+    cudaEventDestroy(t->ev_join);
   if (t->own_stream)
     cudaStreamDestroy(t->own_stream);
   cudaGetLastError();
@@ -346,6 +645,20 @@ int rt_set_stream(rt_tree* t, void* cuda_stream)
     return fail(RT_E_INVALID, "rt_set_stream: tree is NULL");
   t->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->own_stream;
   return RT_OK;
+}
+
+int rt_set_option(rt_tree* t, uint32_t option, uint64_t value)
+{
+  if (t == nullptr)
+    return fail(RT_E_INVALID, "rt_set_option: tree is NULL");
+  switch (option)
+  {
+  case RT_OPT_PIPELINE_BATCH: t->pipeline_batch = value; return RT_OK;
+  case RT_OPT_QUERY_CHUNK: t->query_chunk = (uint32_t)value; return RT_OK;
+  case RT_OPT_WORK_RANGES: t->work_ranges = (uint32_t)value; return RT_OK;
+  case RT_OPT_TRAVERSE_GRID: t->traverse_grid = (int)value; return RT_OK;
+  default: return fail(RT_E_INVALID, "rt_set_option: unknown option");
+  }
 }
 
 int rt_get_stats(const rt_tree* t, rt_stats* out)
@@ -386,8 +699,9 @@ int rt_query_boxes(rt_tree* t, const void* boxes, uint64_t n, uint32_t mode, uin
                               "(use RT_INTERSECTS or RT_CONTAINS)");
   if (n >= 0xFFFFFFFFull)
     return fail(RT_E_INVALID, "rt_query_boxes: at most 2^32-2 queries per call");
-  rtb::box_launch_fn launch = rtb::find_box_kernel(t->desc.scalar, t->desc.dim, t->desc.width, t->desc.key_kind, mode);
-  if (launch == nullptr)
+  BoxCall c;
+  c.launch = rtb::find_box_kernel(t->desc.scalar, t->desc.dim, t->desc.width, t->desc.key_kind, mode);
+  if (c.launch == nullptr)
     return fail(RT_E_UNSUPPORTED, "rt_query_boxes: no kernel for this tree");
   int rc = use_device(t);
   if (rc != RT_OK)
@@ -395,216 +709,140 @@ int rt_query_boxes(rt_tree* t, const void* boxes, uint64_t n, uint32_t mode, uin
 
   std::memset(out, 0, sizeof *out);
   std::memset(&t->stats, 0, sizeof t->stats);
+  c.query_stride = (size_t)2 * t->desc.dim * (t->desc.scalar == RT_F64 ? 8u : 4u);
+  c.on_device = (flags & RT_QUERIES_ON_DEVICE) != 0;
+  c.keep_on_device = (flags & RT_RESULT_ON_DEVICE) != 0;
+  c.count_only = (flags & RT_COUNT_ONLY) != 0;
+  c.collect = (flags & RT_COLLECT_VISITS) != 0;
+  c.sorted = (flags & RT_UNSORTED) == 0;
+  c.reorder = (flags & RT_NO_REORDER) == 0;
+  c.two_pass = c.collect || c.count_only;
+
+  // ---- how the call is cut into batches ------------------------------------------------------
+  uint64_t n_batches = 1;
+  if (!c.keep_on_device && t->pipeline_batch > 0 && n / t->pipeline_batch >= 2)
+    n_batches = n / t->pipeline_batch;
+  const bool pipelined = n_batches > 1;
+  c.pipelined = pipelined;
+  const uint64_t per_batch = pipelined ? ((n + n_batches - 1) / n_batches + 3) / 4 * 4 : n;
+  if (pipelined)
+    n_batches = (n + per_batch - 1) / per_batch;
+  std::vector<Batch> batches((size_t)n_batches);
+  for (uint64_t k = 0; k < n_batches; ++k)
+  {
+    Batch& b = batches[(size_t)k];
+    b.slot = &t->slot[pipelined ? k % NSLOT : 0];
+    b.st = pipelined ? b.slot->stream : t->stream;
+    b.first = k * per_batch;
+    b.n = (k + 1 == n_batches) ? n - b.first : per_batch;
+    b.queries = static_cast<const unsigned char*>(boxes) + (size_t)b.first * c.query_stride;
+    if ((rc = batch_events(t, (size_t)k, &b.ev)) != RT_OK)
+      return rc;
+  }
+  for (uint64_t k = 0; k < n_batches; ++k) // the vector of events may have moved while growing
+    batches[(size_t)k].ev = t->events.data() + (size_t)k * EV_COUNT;
+  if (!c.keep_on_device)
+  {
+    RT_CUDA(t->h_offsets.reserve((size_t)(n + 1) * sizeof(unsigned long long)));
+    if (pipelined && !c.count_only && t->ids_wanted)
+      RT_CUDA(t->h_ids.reserve((size_t)(t->ids_wanted + t->ids_wanted / 32 + 1024) * sizeof(uint32_t)));
+  }
+
+  // ---- issue ---------------------------------------------------------------------------------
   cudaStream_t st = t->stream;
-  const uint32_t scalar_bytes = t->desc.scalar == RT_F64 ? 8u : 4u;
-  const size_t query_bytes = (size_t)n * 2 * t->desc.dim * scalar_bytes;
-  const bool on_device = (flags & RT_QUERIES_ON_DEVICE) != 0;
-  const bool keep_on_device = (flags & RT_RESULT_ON_DEVICE) != 0;
-  const bool count_only = (flags & RT_COUNT_ONLY) != 0;
-  const bool collect = (flags & RT_COLLECT_VISITS) != 0;
-  const bool sorted = (flags & RT_UNSORTED) == 0;
-  const bool reorder = (flags & RT_NO_REORDER) == 0 && n >= 4096;
-  const bool two_pass = collect || count_only;
-  uint32_t launches = 0;
-
-  // ---- buffers ---------------------------------------------------------------------
-  RT_CUDA(t->d_counts.reserve((size_t)(n + 4) * sizeof(uint32_t)));
-  RT_CUDA(t->d_offsets.reserve((size_t)(n + 1) * sizeof(unsigned long long)));
-  size_t scratch = rtb::scan_scratch_bytes(n);
-  if (reorder)
-    scratch = scratch > rtb::reorder_scratch_bytes(n) ? scratch : rtb::reorder_scratch_bytes(n);
-  RT_CUDA(t->d_scratch.reserve(scratch));
-  RT_CUDA(t->d_big.reserve((size_t)(n + 1) * sizeof(uint32_t)));
-  if (!on_device)
-    RT_CUDA(t->d_queries.reserve(query_bytes ? query_bytes : 16));
-  if (reorder)
-    RT_CUDA(t->d_order.reserve((size_t)n * sizeof(uint32_t)));
-  unsigned long long stash_capacity = 0;
-  if (!two_pass)
+  RT_CUDA(cudaEventRecord(t->ev_fork, st));
+  if (pipelined)
   {
-    RT_CUDA(t->d_stash_pos.reserve((size_t)(n + 1) * sizeof(uint32_t)));
-    RT_CUDA(t->d_deferred.reserve((size_t)(n + 1) * sizeof(uint32_t)));
-    // pool: what the previous call needed (+25%), else ~12 ids per query; never more than a
-    // quarter of the free memory, never more than 32-bit positions can address
-    unsigned long long want = t->stash_wanted ? t->stash_wanted + t->stash_wanted / 4 : n * 12ull;
-    want += 4ull * rtb::STASH_SLAB * 1024;
-    if (want > 0xFFFFF000ull)
-      want = 0xFFFFF000ull;
-    const unsigned long long have = t->d_stash.cap / sizeof(uint32_t);
-    if (want > have)
+    for (Slot& s : t->slot)
+      RT_CUDA(cudaStreamWaitEvent(s.stream, t->ev_fork, 0));
+  }
+  unsigned long long total = 0;
+  uint64_t done_queries = 0;
+  const uint64_t lag = pipelined ? NSLOT - 1 : 0;
+  for (uint64_t k = 0; k < n_batches + lag; ++k)
+  {
+    if (k < n_batches && (rc = box_issue_count(t, c, batches[(size_t)k])) != RT_OK)
+      return rc;
+    if (k < lag)
+      continue;
+    Batch& b = batches[(size_t)(k - lag)];
+    if ((rc = box_wait_counted(b)) != RT_OK)
+      return rc;
+    if (!c.keep_on_device && !c.count_only)
     {
-      // growing: cap the pool at a quarter of the free memory (cudaMemGetInfo costs
-      // milliseconds, so it is only asked when the pool really has to grow)
-      size_t free_b = 0, total_b = 0;
-      RT_CUDA(cudaMemGetInfo(&free_b, &total_b));
-      const unsigned long long limit = (unsigned long long)(free_b / 4 / sizeof(uint32_t)) + have;
-      if (want > limit)
-        want = limit;
+      // size the pinned id buffer: exactly for a single batch, by extrapolation while batches
+      // are still to come (the first call of a size pays for the growth, later ones do not)
+      const unsigned long long need = total + b.hc.total;
+      unsigned long long hint = need;
+      if (pipelined)
+      {
+        const double seen = (double)(done_queries + b.n);
+        hint = (unsigned long long)((double)need / (seen > 0 ? seen : 1.0) * (double)n * 1.03) + 4096;
+      }
+      if ((rc = grow_host_ids(t, need ? need : 1, total, hint)) != RT_OK)
+        return rc;
     }
-    if (want > have)
+    if ((rc = box_issue_write(t, c, b, total, k - lag + 1 == n_batches)) != RT_OK)
+      return rc;
+    total += b.hc.total;
+    done_queries += b.n;
+  }
+  if (pipelined)
+  {
+    for (Slot& s : t->slot)
     {
-      cudaError_t e = t->d_stash.reserve((size_t)want * sizeof(uint32_t));
-      if (e != cudaSuccess)
-        cudaGetLastError(); // keep whatever we have; overflowing queries are deferred
+      RT_CUDA(cudaEventRecord(s.done, s.stream));
+      RT_CUDA(cudaStreamWaitEvent(st, s.done, 0));
     }
-    stash_capacity = t->d_stash.cap / sizeof(uint32_t);
-    if (stash_capacity > 0xFFFFF000ull)
-      stash_capacity = 0xFFFFF000ull;
-    // test knob: pretend the pool is this small so the exhaustion path can be exercised
-    if (const char* limit = std::getenv("RTB_STASH_LIMIT_IDS"))
-    {
-      const unsigned long long cap = std::strtoull(limit, nullptr, 10);
-      if (cap < stash_capacity)
-        stash_capacity = cap;
-    }
+    t->ids_wanted = total;
   }
-
-  // ---- H2D ---------------------------------------------------------------------------
-  RT_CUDA(cudaEventRecord(t->ev[EV_BEGIN], st));
-  const void* d_q = boxes;
-  if (!on_device)
-  {
-    if (query_bytes)
-      RT_CUDA(cudaMemcpyAsync(t->d_queries.p, boxes, query_bytes, cudaMemcpyHostToDevice, st));
-    d_q = t->d_queries.p;
-  }
-  RT_CUDA(cudaMemsetAsync(t->d_counters.p, 0, sizeof(Counters), st));
-  RT_CUDA(cudaEventRecord(t->ev[EV_H2D], st));
-
-  // ---- coherence pass ----------------------------------------------------------------
-  const uint32_t* d_order = nullptr;
-  if (reorder)
-  {
-    RT_CUDA(rtb::launch_reorder(d_q, t->desc.scalar, t->desc.dim, 2 * t->desc.dim, n, t->d_order.as<uint32_t>(),
-                                t->d_scratch.p, st, &launches));
-    d_order = t->d_order.as<uint32_t>();
-  }
-  RT_CUDA(cudaEventRecord(t->ev[EV_REORDER], st));
-
-  // ---- first traversal -----------------------------------------------------------------
-  Counters* dc = t->d_counters.as<Counters>();
-  rtb::BoxLaunch L;
-  std::memset(&L, 0, sizeof L);
-  L.tree = t->dev;
-  L.queries = d_q;
-  L.order = d_order;
-  L.n = n;
-  L.counts = t->d_counts.as<uint32_t>();
-  L.offsets = t->d_offsets.as<unsigned long long>();
-  L.stash = t->d_stash.as<uint32_t>();
-  L.stash_pos = t->d_stash_pos.as<uint32_t>();
-  L.stash_capacity = stash_capacity;
-  L.stash_cursor = &dc->stash_cursor;
-  L.deferred_list = t->d_deferred.as<uint32_t>();
-  L.deferred_count = &dc->deferred;
-  L.big_list = t->d_big.as<uint32_t>();
-  L.big_count = &dc->big;
-  L.work_counter = &dc->work;
-  L.visit_stats = dc->visits;
-  L.sorted = sorted ? 1u : 0u;
-  L.stream = st;
-  L.pass = two_pass ? (collect ? rtb::PASS_COUNT_STATS : rtb::PASS_COUNT) : rtb::PASS_STASH;
-  if (n > 0)
-  {
-    RT_CUDA(launch(L));
-    ++launches;
-  }
-  RT_CUDA(cudaEventRecord(t->ev[EV_TRAVERSE], st));
-
-  // ---- CSR offsets, then the 64-byte read-back that sizes the id buffer -----------------
-  RT_CUDA(rtb::launch_exclusive_scan(t->d_counts.as<uint32_t>(), n, t->d_offsets.as<unsigned long long>(),
-                                     t->d_scratch.p, st, &launches));
-  RT_CUDA(cudaMemcpyAsync(&dc->total, t->d_offsets.as<unsigned long long>() + n, sizeof(unsigned long long),
-                          cudaMemcpyDeviceToDevice, st));
-  RT_CUDA(cudaMemcpyAsync(t->h_counters.p, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaEventRecord(t->ev_join, st));
   RT_CUDA(cudaStreamSynchronize(st));
-  Counters hc = *t->h_counters.as<Counters>();
-  const unsigned long long total = hc.total;
-  uint32_t deferred = 0;
-  if (!two_pass)
-    t->stash_wanted = hc.stash_cursor;
 
-  if (!count_only)
-  {
-    RT_CUDA(t->d_ids.reserve((size_t)(total ? total : 1) * sizeof(uint32_t)));
-    RT_CUDA(cudaEventRecord(t->ev_t2_begin, st));
-    bool second = false;
-    if (two_pass)
-    {
-      second = n > 0 && total > 0;
-      L.order = d_order;
-      L.n = n;
-      deferred = (uint32_t)n;
-    }
-    else
-    {
-      RT_CUDA(rtb::launch_gather_stash(t->d_stash.as<uint32_t>(), t->d_stash_pos.as<uint32_t>(),
-                                       t->d_offsets.as<unsigned long long>(), n, t->d_ids.as<uint32_t>(), st,
-                                       &launches));
-      deferred = hc.deferred;
-      second = deferred > 0;
-      L.order = t->d_deferred.as<uint32_t>();
-      L.n = deferred;
-    }
-    if (second)
-    {
-      RT_CUDA(cudaMemsetAsync(&dc->work, 0, sizeof(unsigned long long), st));
-      L.pass = rtb::PASS_WRITE;
-      L.ids = t->d_ids.as<uint32_t>();
-      RT_CUDA(launch(L));
-      ++launches;
-      if (sorted)
-        RT_CUDA(rtb::launch_sort_segments(t->d_big.as<uint32_t>(), &dc->big, (uint32_t)L.n,
-                                          t->d_offsets.as<unsigned long long>(), t->d_ids.as<uint32_t>(), st,
-                                          &launches));
-    }
-    RT_CUDA(cudaEventRecord(t->ev_t2_end, st));
-  }
-  RT_CUDA(cudaEventRecord(t->ev[EV_FINISH], st));
-
-  // ---- D2H ---------------------------------------------------------------------------------
+  // ---- result ----------------------------------------------------------------------------------
   out->n_queries = n;
   out->total = total;
-  if (keep_on_device)
+  if (c.keep_on_device)
   {
-    out->offsets = t->d_offsets.as<uint64_t>();
-    out->ids = count_only ? nullptr : t->d_ids.as<uint32_t>();
+    Slot& s = t->slot[0];
+    out->offsets = s.d_offsets.as<uint64_t>();
+    out->ids = c.count_only ? nullptr : s.d_ids.as<uint32_t>();
     out->memory = RT_MEM_DEVICE;
   }
   else
   {
-    RT_CUDA(t->h_offsets.reserve((size_t)(n + 1) * sizeof(unsigned long long)));
-    RT_CUDA(cudaMemcpyAsync(t->h_offsets.p, t->d_offsets.p, (size_t)(n + 1) * sizeof(unsigned long long),
-                            cudaMemcpyDeviceToHost, st));
-    if (!count_only)
-    {
-      RT_CUDA(t->h_ids.reserve((size_t)(total ? total : 1) * sizeof(uint32_t)));
-      if (total)
-        RT_CUDA(cudaMemcpyAsync(t->h_ids.p, t->d_ids.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    }
     out->offsets = t->h_offsets.as<uint64_t>();
-    out->ids = count_only ? nullptr : t->h_ids.as<uint32_t>();
+    out->ids = c.count_only ? nullptr : t->h_ids.as<uint32_t>();
     out->memory = RT_MEM_HOST;
   }
-  RT_CUDA(cudaEventRecord(t->ev[EV_D2H], st));
-  RT_CUDA(cudaStreamSynchronize(st));
 
-  // ---- stats ---------------------------------------------------------------------------------
+  // ---- stats: per-phase times are sums over the batches (they overlap when pipelined) ------------
   rt_stats& s = t->stats;
-  s.total_ms = elapsed(t->ev[EV_BEGIN], t->ev[EV_D2H]);
-  s.h2d_ms = elapsed(t->ev[EV_BEGIN], t->ev[EV_H2D]);
-  s.reorder_ms = elapsed(t->ev[EV_H2D], t->ev[EV_REORDER]);
-  s.traverse_ms = elapsed(t->ev[EV_REORDER], t->ev[EV_TRAVERSE]);
-  s.finish_ms = elapsed(t->ev[EV_TRAVERSE], t->ev[EV_FINISH]);
-  s.d2h_ms = elapsed(t->ev[EV_FINISH], t->ev[EV_D2H]);
-  s.kernel_launches = launches;
-  s.deferred_queries = count_only ? 0 : deferred;
-  if (collect)
+  s.total_ms = elapsed(t->ev_fork, t->ev_join);
+  s.batches = (uint32_t)n_batches;
+  uint64_t v_int = 0, v_leaf = 0;
+  for (const Batch& b : batches)
   {
-    s.visits_internal = hc.visits[0];
-    s.visits_leaf = hc.visits[1];
-    s.traverse_steps = hc.visits[3];
-    s.algorithmic_bytes = algorithmic_bytes_boxes(t, n, total, hc.visits[0], hc.visits[1]);
+    s.h2d_ms += elapsed(b.ev[EV_BEGIN], b.ev[EV_H2D]);
+    s.reorder_ms += elapsed(b.ev[EV_H2D], b.ev[EV_REORDER]);
+    s.traverse_ms += elapsed(b.ev[EV_REORDER], b.ev[EV_TRAVERSE]);
+    s.finish_ms += elapsed(b.ev[EV_TRAVERSE], b.ev[EV_COUNTED]) + elapsed(b.ev[EV_WRITE], b.ev[EV_FINISH]);
+    s.d2h_ms += elapsed(b.ev[EV_FINISH], b.ev[EV_D2H]);
+    s.kernel_launches += b.launches;
+    s.deferred_queries += c.count_only ? 0 : b.deferred;
+    v_int += b.hc.visits[0];
+    v_leaf += b.hc.visits[1];
+    s.traverse_steps += b.hc.visits[3];
+  }
+  if (c.collect)
+  {
+    s.visits_internal = v_int;
+    s.visits_leaf = v_leaf;
+    s.algorithmic_bytes = algorithmic_bytes_boxes(t, n, total, v_int, v_leaf);
+  }
+  else
+  {
+    s.traverse_steps = 0;
   }
   return RT_OK;
 }
@@ -628,6 +866,13 @@ int rt_query_rays(rt_tree* t, const float* rays, uint64_t n, uint32_t mode, uint
   std::memset(out, 0, sizeof *out);
   std::memset(&t->stats, 0, sizeof t->stats);
   cudaStream_t st = t->stream;
+  Slot& w = t->slot[0]; // rays run as one batch on the caller's stream
+  cudaEvent_t* ev = nullptr;
+  if ((rc = batch_events(t, 0, &ev)) != RT_OK)
+    return rc;
+  RT_CUDA(w.d_counters.reserve(sizeof(Counters)));
+  RT_CUDA(w.d_cursors.reserve(rtb::MAX_WORK_RANGES * sizeof(unsigned int)));
+  RT_CUDA(w.h_counters.reserve(sizeof(Counters)));
   const size_t ray_bytes = (size_t)n * 7 * sizeof(float);
   const bool on_device = (flags & RT_QUERIES_ON_DEVICE) != 0;
   const bool keep_on_device = (flags & RT_RESULT_ON_DEVICE) != 0;
@@ -637,13 +882,13 @@ int rt_query_rays(rt_tree* t, const float* rays, uint64_t n, uint32_t mode, uint
   uint32_t launches = 0;
 
   if (!on_device)
-    RT_CUDA(t->d_queries.reserve(ray_bytes ? ray_bytes : 16));
+    RT_CUDA(w.d_queries.reserve(ray_bytes ? ray_bytes : 16));
   if (mode == RT_RAY_ALL_HITS)
   {
-    RT_CUDA(t->d_counts.reserve((size_t)(n + 4) * sizeof(uint32_t)));
-    RT_CUDA(t->d_offsets.reserve((size_t)(n + 1) * sizeof(unsigned long long)));
-    RT_CUDA(t->d_scratch.reserve(rtb::scan_scratch_bytes(n)));
-    RT_CUDA(t->d_big.reserve((size_t)(n + 1) * sizeof(uint32_t)));
+    RT_CUDA(w.d_counts.reserve((size_t)(n + 4) * sizeof(uint32_t)));
+    RT_CUDA(w.d_offsets.reserve((size_t)(n + 1) * sizeof(unsigned long long)));
+    RT_CUDA(w.d_scratch.reserve(rtb::scan_scratch_bytes(n)));
+    RT_CUDA(w.d_big.reserve((size_t)(n + 1) * sizeof(uint32_t)));
   }
   else if (mode == RT_RAY_CLOSEST)
   {
@@ -655,19 +900,19 @@ int rt_query_rays(rt_tree* t, const float* rays, uint64_t n, uint32_t mode, uint
     RT_CUDA(t->d_ray_any.reserve((size_t)n + 16));
   }
 
-  RT_CUDA(cudaEventRecord(t->ev[EV_BEGIN], st));
+  RT_CUDA(cudaEventRecord(ev[EV_BEGIN], st));
   const float* d_rays = rays;
   if (!on_device)
   {
     if (ray_bytes)
-      RT_CUDA(cudaMemcpyAsync(t->d_queries.p, rays, ray_bytes, cudaMemcpyHostToDevice, st));
-    d_rays = t->d_queries.as<float>();
+      RT_CUDA(cudaMemcpyAsync(w.d_queries.p, rays, ray_bytes, cudaMemcpyHostToDevice, st));
+    d_rays = w.d_queries.as<float>();
   }
-  RT_CUDA(cudaMemsetAsync(t->d_counters.p, 0, sizeof(Counters), st));
-  RT_CUDA(cudaEventRecord(t->ev[EV_H2D], st));
-  RT_CUDA(cudaEventRecord(t->ev[EV_REORDER], st));
+  RT_CUDA(cudaMemsetAsync(w.d_counters.p, 0, sizeof(Counters), st));
+  RT_CUDA(cudaEventRecord(ev[EV_H2D], st));
+  RT_CUDA(cudaEventRecord(ev[EV_REORDER], st));
 
-  Counters* dc = t->d_counters.as<Counters>();
+  Counters* dc = w.d_counters.as<Counters>();
   rtb::RayLaunch L;
   std::memset(&L, 0, sizeof L);
   L.tree = t->dev;
@@ -678,14 +923,17 @@ int rt_query_rays(rt_tree* t, const float* rays, uint64_t n, uint32_t mode, uint
   L.n = n;
   L.mode = mode;
   L.pass = collect ? rtb::PASS_COUNT_STATS : rtb::PASS_COUNT;
-  L.counts = t->d_counts.as<uint32_t>();
-  L.offsets = t->d_offsets.as<unsigned long long>();
-  L.big_list = t->d_big.as<uint32_t>();
+  L.counts = w.d_counts.as<uint32_t>();
+  L.offsets = w.d_offsets.as<unsigned long long>();
+  L.big_list = w.d_big.as<uint32_t>();
   L.big_count = &dc->big;
   L.t_out = t->d_ray_t.as<float>();
   L.id_out = t->d_ray_id.as<uint32_t>();
   L.any_out = t->d_ray_any.as<uint8_t>();
-  L.work_counter = &dc->work;
+  L.work.cursors = w.d_cursors.as<unsigned int>();
+  L.work.chunk = t->query_chunk;
+  L.work.ranges = t->work_ranges;
+  L.grid = t->traverse_grid;
   L.visit_stats = dc->visits;
   L.sorted = sorted ? 1u : 0u;
   L.stream = st;
@@ -694,40 +942,39 @@ int rt_query_rays(rt_tree* t, const float* rays, uint64_t n, uint32_t mode, uint
     RT_CUDA(rtb::launch_ray_kernel(L));
     ++launches;
   }
-  RT_CUDA(cudaEventRecord(t->ev[EV_TRAVERSE], st));
+  RT_CUDA(cudaEventRecord(ev[EV_TRAVERSE], st));
 
   Counters hc;
   std::memset(&hc, 0, sizeof hc);
   unsigned long long total = 0;
   if (mode == RT_RAY_ALL_HITS)
   {
-    RT_CUDA(rtb::launch_exclusive_scan(t->d_counts.as<uint32_t>(), n, t->d_offsets.as<unsigned long long>(),
-                                       t->d_scratch.p, st, &launches));
-    RT_CUDA(cudaMemcpyAsync(&dc->total, t->d_offsets.as<unsigned long long>() + n, sizeof(unsigned long long),
+    RT_CUDA(rtb::launch_exclusive_scan(w.d_counts.as<uint32_t>(), n, w.d_offsets.as<unsigned long long>(),
+                                       w.d_scratch.p, st, &launches));
+    RT_CUDA(cudaMemcpyAsync(&dc->total, w.d_offsets.as<unsigned long long>() + n, sizeof(unsigned long long),
                             cudaMemcpyDeviceToDevice, st));
   }
-  RT_CUDA(cudaMemcpyAsync(t->h_counters.p, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaMemcpyAsync(w.h_counters.p, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   RT_CUDA(cudaStreamSynchronize(st));
-  hc = *t->h_counters.as<Counters>();
+  hc = *w.h_counters.as<Counters>();
   total = hc.total;
 
   if (mode == RT_RAY_ALL_HITS && !count_only)
   {
-    RT_CUDA(t->d_ids.reserve((size_t)(total ? total : 1) * sizeof(uint32_t)));
+    RT_CUDA(w.d_ids.reserve((size_t)(total ? total : 1) * sizeof(uint32_t)));
     if (n > 0 && total > 0)
     {
-      RT_CUDA(cudaMemsetAsync(&dc->work, 0, sizeof(unsigned long long), st));
       L.pass = rtb::PASS_WRITE;
-      L.ids = t->d_ids.as<uint32_t>();
+      L.ids = w.d_ids.as<uint32_t>();
       RT_CUDA(rtb::launch_ray_kernel(L));
       ++launches;
       if (sorted)
-        RT_CUDA(rtb::launch_sort_segments(t->d_big.as<uint32_t>(), &dc->big, (uint32_t)n,
-                                          t->d_offsets.as<unsigned long long>(), t->d_ids.as<uint32_t>(), st,
+        RT_CUDA(rtb::launch_sort_segments(w.d_big.as<uint32_t>(), &dc->big, (uint32_t)n,
+                                          w.d_offsets.as<unsigned long long>(), w.d_ids.as<uint32_t>(), st,
                                           &launches));
     }
   }
-  RT_CUDA(cudaEventRecord(t->ev[EV_FINISH], st));
+  RT_CUDA(cudaEventRecord(ev[EV_FINISH], st));
 
   out->n_rays = n;
   out->memory = keep_on_device ? RT_MEM_DEVICE : RT_MEM_HOST;
@@ -739,19 +986,19 @@ int rt_query_rays(rt_tree* t, const float* rays, uint64_t n, uint32_t mode, uint
     out->hits.memory = out->memory;
     if (keep_on_device)
     {
-      out->hits.offsets = t->d_offsets.as<uint64_t>();
-      out->hits.ids = count_only ? nullptr : t->d_ids.as<uint32_t>();
+      out->hits.offsets = w.d_offsets.as<uint64_t>();
+      out->hits.ids = count_only ? nullptr : w.d_ids.as<uint32_t>();
     }
     else
     {
       RT_CUDA(t->h_offsets.reserve((size_t)(n + 1) * sizeof(unsigned long long)));
-      RT_CUDA(cudaMemcpyAsync(t->h_offsets.p, t->d_offsets.p, (size_t)(n + 1) * sizeof(unsigned long long),
+      RT_CUDA(cudaMemcpyAsync(t->h_offsets.p, w.d_offsets.p, (size_t)(n + 1) * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, st));
       if (!count_only)
       {
         RT_CUDA(t->h_ids.reserve((size_t)(total ? total : 1) * sizeof(uint32_t)));
         if (total)
-          RT_CUDA(cudaMemcpyAsync(t->h_ids.p, t->d_ids.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+          RT_CUDA(cudaMemcpyAsync(t->h_ids.p, w.d_ids.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                   st));
       }
       out->hits.offsets = t->h_offsets.as<uint64_t>();
@@ -794,15 +1041,15 @@ int rt_query_rays(rt_tree* t, const float* rays, uint64_t n, uint32_t mode, uint
       out->any = t->h_ray_any.as<uint8_t>();
     }
   }
-  RT_CUDA(cudaEventRecord(t->ev[EV_D2H], st));
+  RT_CUDA(cudaEventRecord(ev[EV_D2H], st));
   RT_CUDA(cudaStreamSynchronize(st));
 
   rt_stats& s = t->stats;
-  s.total_ms = elapsed(t->ev[EV_BEGIN], t->ev[EV_D2H]);
-  s.h2d_ms = elapsed(t->ev[EV_BEGIN], t->ev[EV_H2D]);
-  s.traverse_ms = elapsed(t->ev[EV_REORDER], t->ev[EV_TRAVERSE]);
-  s.finish_ms = elapsed(t->ev[EV_TRAVERSE], t->ev[EV_FINISH]);
-  s.d2h_ms = elapsed(t->ev[EV_FINISH], t->ev[EV_D2H]);
+  s.total_ms = elapsed(ev[EV_BEGIN], ev[EV_D2H]);
+  s.h2d_ms = elapsed(ev[EV_BEGIN], ev[EV_H2D]);
+  s.traverse_ms = elapsed(ev[EV_REORDER], ev[EV_TRAVERSE]);
+  s.finish_ms = elapsed(ev[EV_TRAVERSE], ev[EV_FINISH]);
+  s.d2h_ms = elapsed(ev[EV_FINISH], ev[EV_D2H]);
   s.kernel_launches = launches;
   if (collect && mode == RT_RAY_ALL_HITS)
   {

@@ -128,6 +128,23 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ uint32_t sm_id()
+{
+  uint32_t id;
+  asm("mov.u32 %0, %%smid;" : "=r"(id));
+  return id;
+}
+
+// Claim the next chunk of queries of `range` for this warp (see WorkRanges): the position inside
+// the range, at or beyond per_range when the range is used up.
+__device__ __forceinline__ uint32_t claim_chunk(const WorkRanges& w, uint32_t range, int lane)
+{
+  uint32_t c = 0;
+  if (lane == 0)
+    c = atomicAdd(w.cursors + range, w.chunk);
+  return __shfl_sync(0xFFFFFFFFu, c, 0);
+}
+
 // ascending bitonic sort of one value per lane
 __device__ __forceinline__ uint32_t warp_sort32(uint32_t v, int lane)
 {

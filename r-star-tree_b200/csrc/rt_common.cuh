@@ -39,7 +39,24 @@ constexpr uint32_t HIT_BUF = 32;        // per-warp hit buffer (one id per lane)
 constexpr uint32_t STASH_SLAB = 512;    // ids a warp reserves from the stash per atomic
 constexpr uint32_t NO_STASH = 0xFFFFFFFFu;
 constexpr int TRAVERSE_THREADS = 256;   // 8 warps per CTA
-constexpr uint32_t QUERY_CHUNK = 8;     // queries a warp claims per atomic
+constexpr uint32_t QUERY_CHUNK = 4;     // queries a warp claims per atomic (default)
+constexpr uint32_t MAX_WORK_RANGES = 1u << 16;
+
+// Work distribution of the persistent traversal kernels.  The n queries, in processing order
+// (Morton order after the coherence pass), are cut into `ranges` contiguous ranges of `per_range`
+// queries.  By default there is one range per SM: every warp resident on SM s starts on range s
+// and claims `chunk` consecutive queries at a time from that range's cursor, so the 64 warps of an
+// SM walk one short window of neighbouring queries and find each other's nodes in L1.  A warp
+// whose range is used up steals chunks from the following ranges.  cursors[] is zeroed by the
+// launcher.
+struct WorkRanges
+{
+  unsigned int* cursors; // [ranges], queries handed out per range
+  uint32_t ranges;
+  uint32_t per_range;    // a multiple of chunk
+  uint32_t chunk;
+  uint32_t by_sm;        // start range = %smid % ranges (else blockIdx.x % ranges)
+};
 
 struct BoxLaunch
 {
@@ -60,10 +77,10 @@ struct BoxLaunch
   uint32_t* deferred_count;
   uint32_t* big_list;               // queries whose list must be sorted afterwards (WRITE)
   uint32_t* big_count;
-  unsigned long long* work_counter; // device counter, zeroed before launch
+  WorkRanges work;                  // cursors = MAX_WORK_RANGES entries; the rest is set by the launcher
   unsigned long long* visit_stats;  // [2] internal / leaf visits (COUNT_STATS)
   uint32_t sorted;                  // 0: keep traversal order
-  int grid;                         // 0: pick from occupancy
+  int grid;                         // 0: fill the GPU; > 0: exactly; < 0: fill, less -grid CTAs per SM
   cudaStream_t stream;
 };
 
@@ -94,7 +111,7 @@ struct RayLaunch
   float* t_out;
   uint32_t* id_out;
   uint8_t* any_out;
-  unsigned long long* work_counter;
+  WorkRanges work;
   unsigned long long* visit_stats;
   uint32_t sorted;
   int grid;
@@ -102,11 +119,20 @@ struct RayLaunch
 };
 cudaError_t launch_ray_kernel(const RayLaunch&); // rt_ray.cu; cudaErrorInvalidValue if unsupported
 
+// grid of a persistent traversal launch (occupancy x SMs, clamped to the work) and the split of
+// the n queries into ranges; zeroes the cursors on `stream`.  On entry work.chunk / work.ranges
+// hold the caller's wishes (0 = default: QUERY_CHUNK, one range per SM).
+cudaError_t plan_work(const void* kernel, size_t smem, uint64_t n, int forced_grid, cudaStream_t stream,
+                      WorkRanges& work, int& grid);
+
 // ---- rt_passes.cu -----------------------------------------------------------------
 // offsets[0..n] = exclusive prefix sum of counts[0..n) (64-bit); scratch >= scan_scratch_bytes(n)
 size_t scan_scratch_bytes(uint64_t n);
 cudaError_t launch_exclusive_scan(const uint32_t* counts, uint64_t n, unsigned long long* offsets,
                                   void* scratch, cudaStream_t stream, uint32_t* launches);
+// offsets[0..n) += base (rebases the CSR offsets of one batch of a pipelined call)
+cudaError_t launch_add_base(unsigned long long* offsets, uint64_t n, unsigned long long base,
+                            cudaStream_t stream, uint32_t* launches);
 // ids[offsets[q] + k] = stash[stash_pos[q] + k] for every stashed query
 cudaError_t launch_gather_stash(const uint32_t* stash, const uint32_t* stash_pos,
                                 const unsigned long long* offsets, uint64_t n, uint32_t* ids,

@@ -6,8 +6,63 @@
 // All are bandwidth-trivial next to the traversal (a few bytes per query).
 #include "rt_common.cuh"
 
+#include <cstdlib>
+
 namespace rtb
 {
+
+// ================================ work distribution =================================
+cudaError_t plan_work(const void* kernel, size_t smem, uint64_t n, int forced_grid, cudaStream_t stream,
+                      WorkRanges& work, int& grid)
+{
+  cudaError_t err = cudaSuccess;
+  grid = forced_grid;
+  if (grid <= 0)
+  {
+    // forced_grid < 0: leave that many CTA slots per SM free (pipelined calls: the small kernels
+    // of the neighbouring batches must not queue behind a GPU-filling persistent kernel)
+    const int spare = -forced_grid;
+    int device = 0, sms = 0, per_sm = 0;
+    if ((err = cudaGetDevice(&device)) != cudaSuccess)
+      return err;
+    if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+      return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRAVERSE_THREADS, smem))
+        != cudaSuccess)
+      return err;
+    per_sm = per_sm - spare < 1 ? 1 : per_sm - spare;
+    grid = sms * per_sm; // persistent: every resident warp pulls chunks until none is left
+  }
+  const uint32_t chunk = work.chunk >= 1 && work.chunk <= 1024 ? work.chunk : QUERY_CHUNK;
+  const unsigned long long chunks = (n + chunk - 1) / chunk;
+  const unsigned long long needed = (chunks + TRAVERSE_THREADS / 32 - 1) / (TRAVERSE_THREADS / 32);
+  if ((unsigned long long)grid > needed)
+    grid = (int)(needed > 0 ? needed : 1);
+  // default: one range per SM, warps start on the range of the SM they run on; an explicit
+  // count cuts by CTA index instead (1 = a single global cursor)
+  work.by_sm = work.ranges == 0 ? 1u : 0u;
+  uint32_t ranges = work.ranges;
+  if (ranges == 0)
+  {
+    int device = 0, sms = 0;
+    if ((err = cudaGetDevice(&device)) != cudaSuccess)
+      return err;
+    if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+      return err;
+    ranges = (uint32_t)sms;
+  }
+  if (ranges > (uint32_t)grid && !work.by_sm)
+    ranges = (uint32_t)grid;
+  if (ranges > MAX_WORK_RANGES)
+    ranges = MAX_WORK_RANGES;
+  const unsigned long long per = (n + ranges - 1) / ranges;
+  work.ranges = ranges;
+  work.chunk = chunk;
+  work.per_range = (uint32_t)((per + chunk - 1) / chunk * chunk);
+  if (work.per_range == 0)
+    work.per_range = chunk;
+  return cudaMemsetAsync(work.cursors, 0, (size_t)ranges * sizeof(unsigned int), stream);
+}
 
 // ================================ exclusive scan ====================================
 namespace
@@ -178,6 +233,27 @@ cudaError_t launch_gather_stash(const uint32_t* stash, const uint32_t* stash_pos
   const uint64_t threads = n * 8;
   const uint64_t blocks = (threads + 255) / 256;
   gather_stash_kernel<<<(unsigned)blocks, 256, 0, stream>>>(stash, stash_pos, offsets, n, ids);
+  *launches += 1;
+  return cudaGetLastError();
+}
+
+// ================================ offset rebasing ===================================
+namespace
+{
+__global__ void __launch_bounds__(256) add_base_kernel(unsigned long long* offsets, uint64_t n, unsigned long long base)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    offsets[i] += base;
+}
+} // namespace
+
+cudaError_t launch_add_base(unsigned long long* offsets, uint64_t n, unsigned long long base,
+                            cudaStream_t stream, uint32_t* launches)
+{
+  if (n == 0 || base == 0)
+    return cudaSuccess;
+  add_base_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(offsets, n, base);
   *launches += 1;
   return cudaGetLastError();
 }

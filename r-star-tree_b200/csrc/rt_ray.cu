@@ -17,24 +17,11 @@ cudaError_t launch_ray_mode(const RayLaunch& p)
     if (err != cudaSuccess)
       return err;
   }
-  int grid = p.grid;
-  if (grid <= 0)
-  {
-    int device = 0, sms = 0, per_sm = 0;
-    if ((err = cudaGetDevice(&device)) != cudaSuccess)
-      return err;
-    if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
-      return err;
-    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRAVERSE_THREADS, smem))
-        != cudaSuccess)
-      return err;
-    grid = sms * (per_sm < 1 ? 1 : per_sm);
-  }
-  const unsigned long long chunks = (p.n + QUERY_CHUNK - 1) / QUERY_CHUNK;
-  const unsigned long long needed = (chunks + TRAVERSE_THREADS / 32 - 1) / (TRAVERSE_THREADS / 32);
-  if ((unsigned long long)grid > needed)
-    grid = (int)(needed > 0 ? needed : 1);
-  kernel<<<grid, TRAVERSE_THREADS, smem, p.stream>>>(p);
+  RayLaunch q = p;
+  int grid = 0;
+  if ((err = plan_work((const void*)kernel, smem, p.n, p.grid, p.stream, q.work, grid)) != cudaSuccess)
+    return err;
+  kernel<<<grid, TRAVERSE_THREADS, smem, p.stream>>>(q);
   return cudaGetLastError();
 }
 

@@ -56,17 +56,26 @@ ray_traverse_kernel(const RayLaunch p)
 
   unsigned long long visits_int = 0, visits_leaf = 0, rays_hit = 0, steps = 0;
 
+  uint32_t range = (p.work.by_sm ? sm_id() : blockIdx.x) % p.work.ranges, tries = 0;
   for (;;)
   {
-    unsigned long long first = 0;
-    if (lane == 0)
-      first = atomicAdd(p.work_counter, (unsigned long long)QUERY_CHUNK);
-    first = __shfl_sync(0xFFFFFFFFu, first, 0);
-    if (first >= p.n)
-      break;
-    const unsigned long long last = min(first + (unsigned long long)QUERY_CHUNK, (unsigned long long)p.n);
+    // per_range is a multiple of chunk, so a chunk never crosses its range; n < 2^32 (checked
+    // by the API) but ranges * per_range may exceed it by a little, hence the 64-bit position
+    const uint32_t c = claim_chunk(p.work, range, lane);
+    const unsigned long long begin = (unsigned long long)range * p.work.per_range + c;
+    if (c >= p.work.per_range || begin >= p.n)
+    {
+      // this range is used up: go on to the next one, until all have been seen empty
+      if (++tries >= p.work.ranges)
+        break;
+      range = range + 1 == p.work.ranges ? 0 : range + 1;
+      continue;
+    }
+    const unsigned long long last = min(begin + p.work.chunk, (unsigned long long)p.n);
 
-    for (unsigned long long i = first; i < last; ++i)
+    // (a 64-bit induction variable on purpose: with a 32-bit one ptxas moves the traversal loop's
+    // stack pointer and ballots out of the uniform datapath, which costs 20 % -- measured)
+    for (unsigned long long i = begin; i < last; ++i)
     {
       const unsigned long long qi = p.order ? (unsigned long long)p.order[i] : i;
       float org[D], inv[D];

@@ -245,3 +245,37 @@ def test_config2_scale_properties(rtb):
     for i in sample:                                                       # nothing is missing
         inside = np.all((pts >= q[i, 0]) & (pts <= q[i, 1]), axis=1)
         assert np.array_equal(np.nonzero(inside)[0].astype(np.uint32), ids[off[i]:off[i + 1]])
+
+
+@pytest.mark.parametrize("flags", [0, "visits", "unsorted", "count_only", "no_reorder"])
+def test_pipelined_call_equals_single_batch(rtb, flags):
+    """a host-result call cut into batches that rotate through the working sets (H2D / traversal /
+    D2H of neighbouring batches overlapped) returns the very CSR of the unpipelined call, for every
+    pipeline flavour, ragged last batch and a batch count that is not a multiple of the slots"""
+    flag = {0: 0, "visits": rtb.RT_COLLECT_VISITS, "unsorted": rtb.RT_UNSORTED,
+            "count_only": rtb.RT_COUNT_ONLY, "no_reorder": rtb.RT_NO_REORDER}[flags]
+    n, nq = 60000, 47003
+    pts = rtb.workloads.uniform_points(n, seed=11)
+    q = rtb.workloads.cube_queries(nq, n, seed=12)
+    q[1000:1040, 1] += 0.2  # a run of long hit lists (deferred + segment sort) inside one batch
+    ref = O.RefTree(4).insert(pts).search_boxes(q)
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+        tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, 0)
+        single = tree.query_boxes(q, flags=flag)
+        assert tree.stats()["batches"] == 1
+        single_visits = (tree.stats()["visits_internal"], tree.stats()["visits_leaf"])
+        for batch in (5000, 6500, 20000):
+            tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, batch)
+            for _ in range(2):  # the second call reuses every buffer the first one grew
+                got = tree.query_boxes(q, flags=flag)
+                s = tree.stats()
+                assert s["batches"] == nq // batch and s["batches"] >= 2
+                assert np.array_equal(got[0], single[0]) and np.array_equal(got[1], single[1])
+                if flags == "visits":
+                    assert (s["visits_internal"], s["visits_leaf"]) == single_visits
+        if flags == "unsorted":
+            assert np.array_equal(single[0], ref[0]) and np.array_equal(sort_segments(*single), ref[1])
+        elif flags == "count_only":
+            assert np.array_equal(single[0], ref[0])
+        else:
+            assert csr_equal(single, ref)
