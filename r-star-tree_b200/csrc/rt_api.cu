@@ -238,7 +238,7 @@ int check_desc(const rt_tree_desc* d)
   const uint64_t need = d->leaf_offset + (uint64_t)(d->num_nodes - leaf_begin) * d->leaf_stride;
   if (d->leaf_offset < need_internal || d->blocks_bytes < need)
     return fail(RT_E_INVALID, "rt_upload: blocks_bytes smaller than the layout needs");
-  if (need / 16 >= RT_INVALID_ID)
+  if ((d->blocks_bytes + 4096) / 16 >= RT_INVALID_ID)
     return fail(RT_E_INVALID, "rt_upload: tree image larger than 64 GB");
   if (d->num_values >= RT_INVALID_ID)
     return fail(RT_E_INVALID, "rt_upload: too many values");
@@ -573,7 +573,11 @@ int rt_upload(const rt_tree_desc* desc, int device, rt_tree** out)
     rt_free(t);
     return fail(code, what);
   };
-  cudaError_t e = cudaMalloc((void**)&t->d_blocks, desc->blocks_bytes ? desc->blocks_bytes : 16);
+  // the image is followed by one "null" block whose slots are all empty (every word 0xFFFFFFFF:
+  // link = RT_INVALID_ID); idle lane groups of the traversal kernels read it instead of branching
+  const uint64_t null_offset = (desc->blocks_bytes + 127) / 128 * 128;
+  const uint64_t null_bytes = desc->internal_stride > desc->leaf_stride ? desc->internal_stride : desc->leaf_stride;
+  cudaError_t e = cudaMalloc((void**)&t->d_blocks, null_offset + null_bytes);
   if (e != cudaSuccess)
     return cleanup(RT_E_NOMEM, std::string("rt_upload: cudaMalloc(blocks): ") + cudaGetErrorString(e));
   e = cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking);
@@ -592,6 +596,8 @@ int rt_upload(const rt_tree_desc* desc, int device, rt_tree** out)
                       desc->blocks_memory == RT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                       t->stream);
   if (e == cudaSuccess)
+    e = cudaMemsetAsync(t->d_blocks + null_offset, 0xFF, null_bytes, t->stream);
+  if (e == cudaSuccess)
     e = cudaStreamSynchronize(t->stream);
   if (e != cudaSuccess)
     return cleanup(RT_E_CUDA, std::string("rt_upload: copy of blocks: ") + cudaGetErrorString(e));
@@ -600,6 +606,7 @@ int rt_upload(const rt_tree_desc* desc, int device, rt_tree** out)
   t->desc.blocks_memory = RT_MEM_DEVICE;
   t->dev.blocks = t->d_blocks;
   t->dev.leaf_link_begin = (uint32_t)(desc->leaf_offset / 16);
+  t->dev.null_link = (uint32_t)(null_offset / 16);
   t->dev.num_nodes = desc->num_nodes;
   t->dev.num_levels = desc->num_levels;
   *out = t;

@@ -22,6 +22,7 @@ struct TreeDev
 {
   const unsigned char* blocks; // internal blocks, then (at leaf_offset) leaf blocks
   uint32_t leaf_link_begin;    // leaf_offset / 16
+  uint32_t null_link;          // a block past the leaves whose slots are all empty (appended by rt_upload)
   uint32_t num_nodes;
   uint32_t num_levels;
 };
@@ -57,6 +58,13 @@ struct WorkRanges
   uint32_t chunk;
   uint32_t by_sm;        // start range = %smid % ranges (else blockIdx.x % ranges)
 };
+
+// dynamic shared memory of a traversal CTA: per warp, G = 32/W words holding the null node,
+// the stack (at most 32 entries per level are ever live) and the hit buffer
+inline size_t traverse_smem_bytes(uint32_t num_levels, uint32_t width)
+{
+  return (size_t)(TRAVERSE_THREADS / 32) * (32u / width + 32u * num_levels + HIT_BUF) * sizeof(uint32_t);
+}
 
 struct BoxLaunch
 {

@@ -51,9 +51,19 @@ box_traverse_kernel(const BoxLaunch p)
   const uint32_t grp = lane / W;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
+  // per warp: G words holding the null node, the stack, the hit buffer (32-bit shared addresses)
   const uint32_t stack_cap = 32u * p.tree.num_levels;
-  const uint32_t stack = smem_addr(smem + warp * (stack_cap + HIT_BUF)); // 32-bit shared addresses
+  const uint32_t warp_mem = smem_addr(smem + warp * (G + stack_cap + HIT_BUF));
+  const uint32_t stack = warp_mem + G * 4u;
   const uint32_t hitbuf = stack + stack_cap * 4u;
+  // group g pops the word at stack_pop + 4 * sp, i.e. stack index sp - G + g: with fewer than G
+  // nodes left the lower groups read the null node below the stack (a block of empty slots),
+  // so popping needs no "is this group active" logic at all
+  const uint32_t stack_pop = stack + (grp - G) * 4u;
+  const uint32_t null_link = p.tree.null_link;
+  if (lane < G)
+    sts_u32(warp_mem + lane * 4u, null_link);
+  __syncwarp();
 
   const unsigned char* lane_blocks = opaque(p.tree.blocks + slot * 16); // this lane's element of a row
   const uint32_t leaf_link_begin = p.tree.leaf_link_begin;
@@ -105,26 +115,22 @@ box_traverse_kernel(const BoxLaunch p)
       }
 
       uint32_t count = 0;
-      uint32_t sp = 1;
+      uint32_t sp4 = 4u; // bytes on the stack (kept warp-uniform: it only ever sees ballots)
       if (lane == 0)
         sts_u32(stack, 0u); // the root; its own bound is never tested (reference rtree.hpp:984)
       __syncwarp();
 
-      while (sp > 0)
+      while (sp4 != 0)
       {
-        const uint32_t take = min(sp, (uint32_t)G);
-        sp -= take;
-        // idle groups (fewer than G nodes left) mirror group 0: same addresses, so their
-        // loads coalesce into group 0's and nothing in the loop needs a branch
-        const bool active = grp < take;
-        const uint32_t node = lds_u32(stack + (sp + (active ? grp : 0u)) * 4u);
+        const uint32_t node = lds_u32(stack_pop + sp4);
+        sp4 -= min(sp4, (uint32_t)(G * 4));
         __syncwarp();
 
         const bool is_leaf = node >= leaf_link_begin;
         uint32_t link;
         S lo[D], hi[D];
         load_entry<S, D, W, BOXKEY>(lane_blocks + (unsigned long long)node * 16u, slot, is_leaf, lo, hi, link);
-        bool hit = active && link != RT_INVALID_ID;
+        bool hit = link != RT_INVALID_ID;
 #pragma unroll
         for (int d = 0; d < D; ++d)
         {
@@ -149,16 +155,15 @@ box_traverse_kernel(const BoxLaunch p)
 
         if (PASS == PASS_COUNT_STATS)
         {
-          const uint32_t leaf_nodes = __popc(__ballot_sync(0xFFFFFFFFu, active && is_leaf && slot == 0));
-          visits_leaf += leaf_nodes;
-          visits_int += take - leaf_nodes;
+          visits_leaf += __popc(__ballot_sync(0xFFFFFFFFu, is_leaf && slot == 0 && node != null_link));
+          visits_int += __popc(__ballot_sync(0xFFFFFFFFu, !is_leaf && slot == 0));
           ++steps;
         }
 
         // children to descend: compact onto the stack in lane order (keeps it level-sorted)
         if (hit && !is_leaf)
-          sts_u32(stack + (sp + __popc(m_int & lt_mask)) * 4u, link);
-        sp += __popc(m_int);
+          sts_u32(stack + sp4 + __popc(m_int & lt_mask) * 4u, link);
+        sp4 += __popc(m_int) * 4u;
 
         // leaf entries that satisfy the predicate
         if (m_leaf != 0)
@@ -265,7 +270,7 @@ template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS>
 cudaError_t launch_box_pass(const BoxLaunch& p)
 {
   auto kernel = box_traverse_kernel<S, D, W, BOXKEY, CONTAINS, PASS>;
-  const size_t smem = (size_t)(TRAVERSE_THREADS / 32) * (32u * p.tree.num_levels + HIT_BUF) * sizeof(uint32_t);
+  const size_t smem = traverse_smem_bytes(p.tree.num_levels, W);
   cudaError_t err = cudaSuccess;
   if (smem > 48 * 1024)
   {
