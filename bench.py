@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=2_000_000,
                     help="queries the OpenMP CPU baseline runs (a prefix of the batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rays", type=int, default=int(os.environ.get("RTB_BENCH_RAYS", 64_000_000)),
+                    help="rays of the secondary config-3 section (split evenly over the GPUs); 0 = skip")
     return ap.parse_args()
 
 
@@ -193,6 +195,49 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+def run_rays(args, rtb, torch, dist, device, local_rank, rank, world, stream, barrier):
+    """BASELINE config 3: AABBs of the triangles of the (procedural) teapot mesh, random-direction
+    rays, closest-hit and any-hit.  The 64 M rays are split evenly over the GPUs (the tree is a few
+    hundred kB and is simply uploaded by every rank); value = all rays / max-over-ranks time."""
+    capi, W = rtb.capi, rtb.workloads
+    boxes = W.triangle_aabbs(W.teapot_triangles(1.0))
+    tree = rtb.RTree(5).insert(boxes).flatten_device().upload(local_rank)
+    tree.set_stream(stream.cuda_stream)
+    nr = args.rays // world
+    h_rays = torch.from_numpy(W.random_rays(nr, boxes, seed=44 + 1000 * rank, tmax=1e30)).pin_memory()
+    d_rays = h_rays.to(device)
+    steps, warmup = max(1, min(args.steps, 5)), max(3, min(args.warmup, 3))
+    dev_flags = capi.RT_QUERIES_ON_DEVICE | capi.RT_RESULT_ON_DEVICE
+    out = {"config": "BASELINE config 3: %d triangle AABBs of the teapot mesh (MAX_ENTRIES 8, box keys), %d "
+                     "random-direction rays split over %d GPU(s)" % (len(boxes), nr * world, world),
+           "unit": "rays/s", "steps": steps, "warmup": warmup, "rays_per_gpu": nr}
+    for name, mode, d2h_per_ray in (("closest_hit", capi.RT_RAY_CLOSEST, 8), ("any_hit", capi.RT_RAY_ANY, 1)):
+        res = {}
+        for leg, ptr, flags in (("value", d_rays.data_ptr(), dev_flags), ("e2e", h_rays.data_ptr(), 0)):
+            with torch.cuda.stream(stream):
+                for _ in range(warmup):
+                    tree.query_rays_raw(ptr, nr, mode, flags)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(steps):
+                    r = tree.query_rays_raw(ptr, nr, mode, flags)
+                e1.record(stream)
+                barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            res[leg] = float(nr) * world * steps / (float(ms.item()) * 1e-3)
+            res[leg + "_ms_per_step"] = float(ms.item()) / steps
+        res["hit_fraction"] = r.n_hit / float(nr)
+        res["h2d_bytes_per_step"] = nr * 28 * world
+        res["d2h_bytes_per_step"] = nr * d2h_per_ray * world
+        out[name] = res
+    tree.close()
+    return out
 
 
 # ---------------------------------------------------------------------------------------
@@ -339,6 +384,9 @@ def main():
     d2h_bytes = int((nq + 1) * 8 + out.total * 4 + 64)
     assert checksum == out.total == total_hits, "device and host legs disagree on the hit total"
 
+    # ---- secondary section: BASELINE config 3, rays/s (closest-hit and any-hit) ----------------
+    rays_section = run_rays(args, rtb, torch, dist, device, local_rank, rank, world, stream, barrier) if args.rays > 0 else None
+
     # ---- max over ranks ---------------------------------------------------------------------
     times = torch.tensor([dev_ms, e2e_ms, float(np.mean(traverse_ms))], dtype=torch.float64, device=device)
     sums = torch.tensor([float(launches), float(alg_bytes), float(total_hits)], dtype=torch.float64, device=device)
@@ -415,6 +463,7 @@ def main():
             "setup": {"host_build_s": round(t_build, 2), "flatten_device_s": round(t_flatten, 3),
                       "tree_broadcast_ms": round(t_bcast_ms, 3), "tree_bytes": int(gpu_tree.blocks_bytes)},
             "parity": parity,
+            "rays": rays_section,
         }
         print(json.dumps(line), flush=True)
     gpu_tree.close()

@@ -190,7 +190,7 @@ struct rt_tree
 
   Slot slot[NSLOT];
   DevBuf d_ray_t, d_ray_id, d_ray_any;
-  HostBuf h_offsets, h_ids, h_ray_t, h_ray_id, h_ray_any;
+  HostBuf h_offsets, h_ids, h_ray_t, h_ray_id, h_ray_any, h_batch_counters;
   uint64_t pipeline_batch = DEFAULT_PIPELINE_BATCH;
   uint32_t query_chunk = 0, work_ranges = 0; // 0 = the kernels' defaults
   int traverse_grid = 0;                     // 0 = fill the GPU
@@ -629,7 +629,7 @@ void rt_free(rt_tree* t)
   DevBuf* dev[] = { &t->d_ray_t, &t->d_ray_id, &t->d_ray_any };
   for (DevBuf* b : dev)
     b->release();
-  HostBuf* host[] = { &t->h_offsets, &t->h_ids, &t->h_ray_t, &t->h_ray_id, &t->h_ray_any };
+  HostBuf* host[] = { &t->h_offsets, &t->h_ids, &t->h_ray_t, &t->h_ray_id, &t->h_ray_any, &t->h_batch_counters };
   for (HostBuf* b : host)
     b->release();
   if (t->d_blocks)
@@ -888,6 +888,124 @@ int rt_query_rays(rt_tree* t, const float* rays, uint64_t n, uint32_t mode, uint
   const bool sorted = (flags & RT_UNSORTED) == 0;
   uint32_t launches = 0;
 
+  // ---- closest / any with a host result and many rays: pipelined batches ------------------------
+  // (one kernel per batch; the H2D copy of the next batch and the D2H copy of the previous one
+  // run under it -- at 28 bytes per ray the call is otherwise bound by the H2D copy alone)
+  if (mode != RT_RAY_ALL_HITS && !keep_on_device && t->pipeline_batch > 0 && n / t->pipeline_batch >= 2)
+  {
+    const uint64_t wanted = n / t->pipeline_batch;
+    const uint64_t per_batch = ((n + wanted - 1) / wanted + 15) / 16 * 16; // keeps every copy 16-byte aligned
+    const uint64_t n_batches = (n + per_batch - 1) / per_batch;
+    if (mode == RT_RAY_CLOSEST)
+    {
+      RT_CUDA(t->d_ray_t.reserve((size_t)(n + 1) * sizeof(float)));
+      RT_CUDA(t->d_ray_id.reserve((size_t)(n + 1) * sizeof(uint32_t)));
+      RT_CUDA(t->h_ray_t.reserve((size_t)(n + 1) * sizeof(float)));
+      RT_CUDA(t->h_ray_id.reserve((size_t)(n + 1) * sizeof(uint32_t)));
+    }
+    else
+    {
+      RT_CUDA(t->d_ray_any.reserve((size_t)n + 16));
+      RT_CUDA(t->h_ray_any.reserve((size_t)n + 16));
+    }
+    RT_CUDA(t->h_batch_counters.reserve((size_t)n_batches * sizeof(Counters)));
+    cudaEvent_t* unused = nullptr;
+    if ((rc = batch_events(t, (size_t)n_batches - 1, &unused)) != RT_OK)
+      return rc;
+    RT_CUDA(cudaEventRecord(t->ev_fork, st));
+    for (Slot& s : t->slot)
+      RT_CUDA(cudaStreamWaitEvent(s.stream, t->ev_fork, 0));
+    for (uint64_t k = 0; k < n_batches; ++k)
+    {
+      Slot& s = t->slot[k % NSLOT];
+      cudaStream_t bs = s.stream;
+      cudaEvent_t* bev = t->events.data() + (size_t)k * EV_COUNT;
+      const uint64_t first = k * per_batch;
+      const uint64_t m = (k + 1 == n_batches) ? n - first : per_batch;
+      RT_CUDA(s.d_counters.reserve(sizeof(Counters)));
+      RT_CUDA(s.d_cursors.reserve(rtb::MAX_WORK_RANGES * sizeof(unsigned int)));
+      if (!on_device)
+        RT_CUDA(s.d_queries.reserve((size_t)per_batch * 7 * sizeof(float)));
+      RT_CUDA(cudaEventRecord(bev[EV_BEGIN], bs));
+      const float* d_rays = rays + first * 7;
+      if (!on_device)
+      {
+        RT_CUDA(cudaMemcpyAsync(s.d_queries.p, rays + first * 7, (size_t)m * 7 * sizeof(float),
+                                cudaMemcpyHostToDevice, bs));
+        d_rays = s.d_queries.as<float>();
+      }
+      RT_CUDA(cudaMemsetAsync(s.d_counters.p, 0, sizeof(Counters), bs));
+      RT_CUDA(cudaEventRecord(bev[EV_H2D], bs));
+      Counters* dc = s.d_counters.as<Counters>();
+      rtb::RayLaunch L;
+      std::memset(&L, 0, sizeof L);
+      L.tree = t->dev;
+      L.width = t->desc.width;
+      L.key_kind = t->desc.key_kind;
+      L.rays = d_rays;
+      L.n = m;
+      L.mode = mode;
+      L.t_out = t->d_ray_t.as<float>() + first;
+      L.id_out = t->d_ray_id.as<uint32_t>() + first;
+      L.any_out = t->d_ray_any.as<uint8_t>() + first;
+      L.work.cursors = s.d_cursors.as<unsigned int>();
+      L.work.chunk = t->query_chunk;
+      L.work.ranges = t->work_ranges;
+      L.grid = t->traverse_grid ? t->traverse_grid : -1;
+      L.visit_stats = dc->visits;
+      L.sorted = 1u;
+      L.stream = bs;
+      RT_CUDA(rtb::launch_ray_kernel(L));
+      ++launches;
+      RT_CUDA(cudaEventRecord(bev[EV_TRAVERSE], bs));
+      RT_CUDA(cudaMemcpyAsync(t->h_batch_counters.as<Counters>() + k, dc, sizeof(Counters), cudaMemcpyDeviceToHost, bs));
+      if (mode == RT_RAY_CLOSEST)
+      {
+        RT_CUDA(cudaMemcpyAsync(t->h_ray_t.as<float>() + first, L.t_out, (size_t)m * sizeof(float),
+                                cudaMemcpyDeviceToHost, bs));
+        RT_CUDA(cudaMemcpyAsync(t->h_ray_id.as<uint32_t>() + first, L.id_out, (size_t)m * sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost, bs));
+      }
+      else
+      {
+        RT_CUDA(cudaMemcpyAsync(t->h_ray_any.as<uint8_t>() + first, L.any_out, (size_t)m, cudaMemcpyDeviceToHost, bs));
+      }
+      RT_CUDA(cudaEventRecord(bev[EV_D2H], bs));
+    }
+    for (Slot& s : t->slot)
+    {
+      RT_CUDA(cudaEventRecord(s.done, s.stream));
+      RT_CUDA(cudaStreamWaitEvent(st, s.done, 0));
+    }
+    RT_CUDA(cudaEventRecord(t->ev_join, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+
+    out->n_rays = n;
+    out->memory = RT_MEM_HOST;
+    if (mode == RT_RAY_CLOSEST)
+    {
+      out->t = t->h_ray_t.as<float>();
+      out->id = t->h_ray_id.as<uint32_t>();
+    }
+    else
+    {
+      out->any = t->h_ray_any.as<uint8_t>();
+    }
+    rt_stats& rs = t->stats;
+    rs.total_ms = elapsed(t->ev_fork, t->ev_join);
+    rs.batches = (uint32_t)n_batches;
+    rs.kernel_launches = launches;
+    for (uint64_t k = 0; k < n_batches; ++k)
+    {
+      cudaEvent_t* bev = t->events.data() + (size_t)k * EV_COUNT;
+      rs.h2d_ms += elapsed(bev[EV_BEGIN], bev[EV_H2D]);
+      rs.traverse_ms += elapsed(bev[EV_H2D], bev[EV_TRAVERSE]);
+      rs.d2h_ms += elapsed(bev[EV_TRAVERSE], bev[EV_D2H]);
+      out->n_hit += t->h_batch_counters.as<Counters>()[k].visits[2];
+    }
+    return RT_OK;
+  }
+
   if (!on_device)
     RT_CUDA(w.d_queries.reserve(ray_bytes ? ray_bytes : 16));
   if (mode == RT_RAY_ALL_HITS)
@@ -1053,6 +1171,7 @@ int rt_query_rays(rt_tree* t, const float* rays, uint64_t n, uint32_t mode, uint
 
   rt_stats& s = t->stats;
   s.total_ms = elapsed(ev[EV_BEGIN], ev[EV_D2H]);
+  s.batches = 1;
   s.h2d_ms = elapsed(ev[EV_BEGIN], ev[EV_H2D]);
   s.traverse_ms = elapsed(ev[EV_REORDER], ev[EV_TRAVERSE]);
   s.finish_ms = elapsed(ev[EV_TRAVERSE], ev[EV_FINISH]);

@@ -9,7 +9,7 @@ template <int W, bool BOXKEY, uint32_t RMODE>
 cudaError_t launch_ray_mode(const RayLaunch& p)
 {
   auto kernel = ray_traverse_kernel<W, BOXKEY, RMODE>;
-  const size_t smem = (size_t)(TRAVERSE_THREADS / 32) * (32u * p.tree.num_levels + HIT_BUF) * sizeof(uint32_t);
+  const size_t smem = traverse_smem_bytes(p.tree.num_levels, W);
   cudaError_t err = cudaSuccess;
   if (smem > 48 * 1024)
   {

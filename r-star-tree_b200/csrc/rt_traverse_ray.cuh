@@ -47,9 +47,16 @@ ray_traverse_kernel(const RayLaunch p)
   const uint32_t grp = lane / W;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
+  // per warp: G words holding the null node, the stack, the hit buffer (see rt_traverse_box.cuh)
   const uint32_t stack_cap = 32u * p.tree.num_levels;
-  const uint32_t stack = smem_addr(smem + warp * (stack_cap + HIT_BUF));
+  const uint32_t warp_mem = smem_addr(smem + warp * (G + stack_cap + HIT_BUF));
+  const uint32_t stack = warp_mem + G * 4u;
   const uint32_t hitbuf = stack + stack_cap * 4u;
+  const uint32_t stack_pop = stack + (grp - G) * 4u; // group g pops stack index sp - G + g
+  const uint32_t null_link = p.tree.null_link;
+  if (lane < G)
+    sts_u32(warp_mem + lane * 4u, null_link);
+  __syncwarp();
 
   const unsigned char* lane_blocks = opaque(p.tree.blocks + slot * 16); // this lane's element of a row
   const uint32_t leaf_link_begin = p.tree.leaf_link_begin;
@@ -101,19 +108,16 @@ ray_traverse_kernel(const RayLaunch p)
       uint32_t id_best = RT_INVALID_ID;
       bool found = false;
       uint32_t count = 0;
-      uint32_t sp = 1;
+      uint32_t sp4 = 4u; // bytes on the stack (warp-uniform)
       if (lane == 0)
         sts_u32(stack, 0u);
       __syncwarp();
 
-      while (sp > 0)
+      while (sp4 != 0)
       {
-        const uint32_t take = min(sp, (uint32_t)G);
-        sp -= take;
-        // idle groups (fewer than G nodes left) mirror group 0: same addresses, so their
-        // loads coalesce into group 0's and nothing in the loop needs a branch
-        const bool active = grp < take;
-        const uint32_t node = lds_u32(stack + (sp + (active ? grp : 0u)) * 4u);
+        // with fewer than G nodes left the lower groups read the null node (all slots empty)
+        const uint32_t node = lds_u32(stack_pop + sp4);
+        sp4 -= min(sp4, (uint32_t)(G * 4));
         __syncwarp();
 
         const bool is_leaf = node >= leaf_link_begin;
@@ -132,7 +136,7 @@ ray_traverse_kernel(const RayLaunch p)
           t0 = (tn > t0) ? tn : t0;
           t1 = (tf < t1) ? tf : t1;
         }
-        bool hit = active && (link != RT_INVALID_ID) && (t0 <= t1);
+        bool hit = (link != RT_INVALID_ID) && (t0 <= t1);
         if (RMODE == RAY_CLOSEST)
           hit = hit && (is_leaf || t0 <= t_best);
 
@@ -142,15 +146,14 @@ ray_traverse_kernel(const RayLaunch p)
 
         if (RMODE == RAY_COUNT_STATS)
         {
-          const uint32_t leaf_nodes = __popc(__ballot_sync(0xFFFFFFFFu, active && is_leaf && slot == 0));
-          visits_leaf += leaf_nodes;
-          visits_int += take - leaf_nodes;
+          visits_leaf += __popc(__ballot_sync(0xFFFFFFFFu, is_leaf && slot == 0 && node != null_link));
+          visits_int += __popc(__ballot_sync(0xFFFFFFFFu, !is_leaf && slot == 0));
           ++steps;
         }
 
         if (hit && !is_leaf)
-          sts_u32(stack + (sp + __popc(m_int & lt_mask)) * 4u, link);
-        sp += __popc(m_int);
+          sts_u32(stack + sp4 + __popc(m_int & lt_mask) * 4u, link);
+        sp4 += __popc(m_int) * 4u;
 
         if (m_leaf != 0)
         {
@@ -172,7 +175,7 @@ ray_traverse_kernel(const RayLaunch p)
           else if (RMODE == RAY_ANY)
           {
             found = true;
-            sp = 0; // abort the whole search
+            sp4 = 0; // abort the whole search
           }
           else
           {

@@ -157,22 +157,26 @@ def triangle_aabbs(tris):
     return np.stack([tris.min(axis=1), tris.max(axis=1)], axis=1).astype(np.float32)
 
 
-def random_rays(n, boxes, seed=44, tmax=np.inf):
+def random_rays(n, boxes, seed=44, tmax=np.inf, threads=None):
     """Rays [n][7] = origin, 1/direction, tmax.
 
     Origins are uniform on the sphere of 3x the scene's bounding radius; directions are
     uniformly random unit vectors conditioned on hitting the scene's bounding sphere (drawn
     directly inside the subtended cone, which is the same distribution as re-drawing until hit).
+    Generated in 1 Mi-ray chunks, chunk c from its own generator seeded (seed, c), so the result
+    does not depend on how many threads filled it.
     """
-    rng = np.random.default_rng(seed)
     lo = boxes[:, 0, :].min(axis=0).astype(np.float64)
     hi = boxes[:, 1, :].max(axis=0).astype(np.float64)
     centre = 0.5 * (lo + hi)
     radius = 0.5 * float(np.linalg.norm(hi - lo))
     out = np.empty((n, 7), np.float32)
     step = 1 << 20
-    for s in range(0, n, step):
+
+    def fill(c):
+        s = c * step
         m = min(step, n - s)
+        rng = np.random.default_rng([seed, c])
         v = rng.normal(size=(m, 3))
         v /= np.linalg.norm(v, axis=1, keepdims=True)
         origin = centre + 3.0 * radius * v
@@ -191,4 +195,16 @@ def random_rays(n, boxes, seed=44, tmax=np.inf):
         with np.errstate(divide="ignore"):
             out[s:s + m, 3:6] = np.float32(1.0) / d32
         out[s:s + m, 6] = np.float32(tmax)
+
+    chunks = range((n + step - 1) // step)
+    if threads is None:
+        import os
+        threads = min(16, os.cpu_count() or 1)
+    if threads > 1 and len(chunks) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(threads) as pool:
+            list(pool.map(fill, chunks))
+    else:
+        for c in chunks:
+            fill(c)
     return out

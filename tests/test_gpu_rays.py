@@ -105,3 +105,25 @@ def test_rays_need_a_3d_f32_tree(rtb):
         with pytest.raises(rtb.RtError) as err:
             tree.query_rays(np.zeros((1, 7), np.float32), rtb.RT_RAY_ANY)
         assert err.value.code == rtb.capi.RT_E_UNSUPPORTED
+
+
+def test_pipelined_ray_batches_equal_single_batch(rtb):
+    """closest / any calls with a host result are cut into batches whose copies overlap the
+    traversal of their neighbours; results and hit counts equal the unpipelined call and the
+    reference's search()"""
+    boxes = rtb.workloads.triangle_aabbs(rtb.workloads.teapot_triangles(1.0))
+    rays = rtb.workloads.random_rays(50_003, boxes, seed=45, tmax=1e30)
+    ref = O.RefTree(5).insert(boxes)
+    want_t, want_id = ref.search_rays(rays, O.RAY_CLOSEST)
+    want_any = ref.search_rays(rays, O.RAY_ANY)
+    with rtb.RTree(5).insert(boxes).flatten_device().upload(0) as tree:
+        for batch in (0, 4000, 7001, 20000):
+            tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, batch)
+            for _ in range(2):
+                r = np.ascontiguousarray(rays)
+                out = tree.query_rays_raw(r.ctypes.data, len(r), rtb.RT_RAY_CLOSEST, 0)
+                assert tree.stats()["batches"] == (max(1, len(r) // batch) if batch else 1)
+                assert out.n_hit == int((want_id != 0xFFFFFFFF).sum())
+                t, tid = tree.query_rays(rays, rtb.RT_RAY_CLOSEST)
+                assert np.array_equal(t.view(np.uint32), want_t.view(np.uint32)) and np.array_equal(tid, want_id)
+                assert np.array_equal(tree.query_rays(rays, rtb.RT_RAY_ANY), want_any)
