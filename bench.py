@@ -260,6 +260,7 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the ONE JSON line only
         dist.init_process_group("nccl", device_id=device)
 
     def barrier():
