@@ -229,6 +229,11 @@ int rt_get_stats(const rt_tree* tree, rt_stats* out);
 /* RT_OPT_TRAVERSE_GRID: CTAs of the persistent traversal kernels; 0 (default) = as many as are
  *   resident at once (SMs x occupancy; one CTA slot per SM is left free in pipelined calls).    */
 #define RT_OPT_TRAVERSE_GRID 4u
+/* RT_OPT_QUANTISED: 1 (default) = box queries on 3-D float32 point-keyed trees with 8-wide blocks
+ *   traverse the quantised image rt_upload builds for them (16-byte slot records with conservative
+ *   15-bit bounds; leaf candidates are confirmed on the float records, so results are identical);
+ *   0 = always the float blocks.  RT_COLLECT_VISITS always uses the float blocks.            */
+#define RT_OPT_QUANTISED 5u
 int rt_set_option(rt_tree* tree, uint32_t option, uint64_t value);
 /* Device copy of the blocks, e.g. to broadcast the tree to peer GPUs.               */
 int rt_tree_device_blocks(const rt_tree* tree, void** device_ptr, uint64_t* bytes);

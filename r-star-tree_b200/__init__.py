@@ -22,7 +22,7 @@ from .capi import (DeviceTree, RtError, RT_POINT_IN_BOX, RT_INTERSECTS, RT_CONTA
                    RT_RAY_ALL_HITS, RT_RAY_CLOSEST, RT_RAY_ANY, RT_QUERIES_ON_DEVICE,
                    RT_RESULT_ON_DEVICE, RT_UNSORTED, RT_COUNT_ONLY, RT_COLLECT_VISITS,
                    RT_NO_REORDER, RT_INVALID_ID, RT_OPT_PIPELINE_BATCH, RT_OPT_QUERY_CHUNK,
-                   RT_OPT_WORK_RANGES)
+                   RT_OPT_WORK_RANGES, RT_OPT_QUANTISED)
 from .host import RTree, DeviceImage, KINDS  # noqa: F401
 
 __all__ = ["capi", "host", "sharding", "workloads", "DeviceTree", "RtError", "RTree",

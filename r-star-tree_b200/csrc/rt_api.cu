@@ -183,6 +183,8 @@ struct rt_tree
   std::vector<uint32_t> levels;
   rtb::TreeDev dev;
   unsigned char* d_blocks = nullptr;
+  unsigned char* d_qblocks = nullptr; // quantised image (3-D float32 point trees, W = 8), else NULL
+  bool use_quant = true;              // RT_OPT_QUANTISED
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -397,6 +399,8 @@ int box_issue_count(rt_tree* t, const BoxCall& c, Batch& b)
   rtb::BoxLaunch& L = b.L;
   std::memset(&L, 0, sizeof L);
   L.tree = t->dev;
+  if (!t->use_quant)
+    L.tree.qblocks = nullptr;
   L.queries = d_q;
   L.order = b.d_order;
   L.n = n;
@@ -609,6 +613,17 @@ int rt_upload(const rt_tree_desc* desc, int device, rt_tree** out)
   t->dev.null_link = (uint32_t)(null_offset / 16);
   t->dev.num_nodes = desc->num_nodes;
   t->dev.num_levels = desc->num_levels;
+  if (desc->scalar == RT_F32 && desc->dim == 3 && desc->width == 8 && desc->key_kind == RT_KEY_POINT
+      && std::getenv("RTB_NO_QUANT") == nullptr)
+  {
+    e = cudaMalloc((void**)&t->d_qblocks, rtb::quant_image_bytes(desc->num_nodes));
+    if (e != cudaSuccess)
+      return cleanup(RT_E_NOMEM, std::string("rt_upload: cudaMalloc(quantised image): ") + cudaGetErrorString(e));
+    e = rtb::build_quant_image(t->dev, desc->level_node_begin[desc->leaf_level], desc->leaf_offset, t->d_qblocks,
+                               t->stream);
+    if (e != cudaSuccess)
+      return cleanup(RT_E_CUDA, std::string("rt_upload: quantised image: ") + cudaGetErrorString(e));
+  }
   *out = t;
   return RT_OK;
 }
@@ -634,6 +649,8 @@ void rt_free(rt_tree* t)
     b->release();
   if (t->d_blocks)
     cudaFree(t->d_blocks);
+  if (t->d_qblocks)
+    cudaFree(t->d_qblocks);
   for (cudaEvent_t e : t->events)
     cudaEventDestroy(e);
   if (t->ev_fork)
@@ -664,6 +681,7 @@ int rt_set_option(rt_tree* t, uint32_t option, uint64_t value)
   case RT_OPT_QUERY_CHUNK: t->query_chunk = (uint32_t)value; return RT_OK;
   case RT_OPT_WORK_RANGES: t->work_ranges = (uint32_t)value; return RT_OK;
   case RT_OPT_TRAVERSE_GRID: t->traverse_grid = (int)value; return RT_OK;
+  case RT_OPT_QUANTISED: t->use_quant = value != 0; return RT_OK;
   default: return fail(RT_E_INVALID, "rt_set_option: unknown option");
   }
 }

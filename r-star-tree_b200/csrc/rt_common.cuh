@@ -23,6 +23,14 @@ struct TreeDev
   const unsigned char* blocks; // internal blocks, then (at leaf_offset) leaf blocks
   uint32_t leaf_link_begin;    // leaf_offset / 16
   uint32_t null_link;          // a block past the leaves whose slots are all empty (appended by rt_upload)
+  // Quantised image (rt_quant.cuh; 3-D float32 point-keyed trees with W = 8 only, else NULL): one
+  // 128-byte block per node -- internal nodes first, then from qleaf_link_begin the leaves in the
+  // order of `blocks` -- whose 16-byte slot records hold conservative 15-bit bounds + the link.
+  const unsigned char* qblocks;
+  const unsigned char* leaf_blocks; // blocks + leaf_offset: the exact records behind the leaf slots
+  uint32_t qleaf_link_begin;
+  uint32_t qnull_link;
+  float qlo[3], qscale[3];          // the grid: q(v) = clamp(floor((v - qlo) * qscale) + 1, 1, 32767)
   uint32_t num_nodes;
   uint32_t num_levels;
 };
@@ -59,8 +67,8 @@ struct WorkRanges
   uint32_t by_sm;        // start range = %smid % ranges (else blockIdx.x % ranges)
 };
 
-// dynamic shared memory of a traversal CTA: per warp, G = 32/W words holding the null node,
-// the stack (at most 32 entries per level are ever live) and the hit buffer
+// dynamic shared memory of a traversal CTA: per warp, the hit buffer, G = 32/W words holding the
+// null node and the stack (at most 32 entries per level are ever live)
 inline size_t traverse_smem_bytes(uint32_t num_levels, uint32_t width)
 {
   return (size_t)(TRAVERSE_THREADS / 32) * (32u / width + 32u * num_levels + HIT_BUF) * sizeof(uint32_t);
@@ -132,6 +140,13 @@ cudaError_t launch_ray_kernel(const RayLaunch&); // rt_ray.cu; cudaErrorInvalidV
 // hold the caller's wishes (0 = default: QUERY_CHUNK, one range per SM).
 cudaError_t plan_work(const void* kernel, size_t smem, uint64_t n, int forced_grid, cudaStream_t stream,
                       WorkRanges& work, int& grid);
+
+// rt_quant.cu: build the quantised image of a 3-D float32 point-keyed W = 8 tree.  `qblocks` must hold
+// quant_image_bytes(num_nodes) bytes; fills tree.qblocks / leaf_blocks / qleaf_link_begin /
+// qnull_link / qlo / qscale (synchronises the stream once to read the grid back).
+size_t quant_image_bytes(uint32_t num_nodes);
+cudaError_t build_quant_image(TreeDev& tree, uint32_t num_internal, uint64_t leaf_offset, unsigned char* qblocks,
+                              cudaStream_t stream);
 
 // ---- rt_passes.cu -----------------------------------------------------------------
 // offsets[0..n] = exclusive prefix sum of counts[0..n) (64-bit); scratch >= scan_scratch_bytes(n)

@@ -32,16 +32,23 @@
 // PASS_WRITE: hit ids go to their final CSR position; short lists are sorted in the warp.
 #pragma once
 
+#include <type_traits>
+
 #include "rt_block.cuh"
 #include "rt_common.cuh"
+#include "rt_quant.cuh"
 
 namespace rtb
 {
 
-template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS>
+// QUANT: traverse the quantised image (rt_quant.cuh) -- one 16-byte record per slot, one integer
+// test for internal children and leaf points alike, leaf candidates confirmed on the float record.
+template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS, bool QUANT = false>
 __global__ void __launch_bounds__(TRAVERSE_THREADS)
 box_traverse_kernel(const BoxLaunch p)
 {
+  static_assert(!QUANT || (std::is_same<S, float>::value && D == 3 && W == 8 && !BOXKEY && PASS != PASS_COUNT_STATS),
+                "the quantised image exists for 3-D float32 point trees with 8-wide blocks");
   constexpr int G = 32 / W;
   extern __shared__ uint32_t smem[];
 
@@ -51,22 +58,26 @@ box_traverse_kernel(const BoxLaunch p)
   const uint32_t grp = lane / W;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
-  // per warp: G words holding the null node, the stack, the hit buffer (32-bit shared addresses)
+  // per warp: the hit buffer, G words holding the null node, the stack (32-bit shared addresses;
+  // the hit buffer sits at a constant distance below the stack so it needs no register of its own)
   const uint32_t stack_cap = 32u * p.tree.num_levels;
-  const uint32_t warp_mem = smem_addr(smem + warp * (G + stack_cap + HIT_BUF));
-  const uint32_t stack = warp_mem + G * 4u;
-  const uint32_t hitbuf = stack + stack_cap * 4u;
+  const uint32_t warp_mem = smem_addr(smem + warp * (HIT_BUF + G + stack_cap));
+  const uint32_t stack = warp_mem + (HIT_BUF + G) * 4u;
+#define hitbuf (stack - (HIT_BUF + G) * 4u)
   // group g pops the word at stack_pop + 4 * sp, i.e. stack index sp - G + g: with fewer than G
   // nodes left the lower groups read the null node below the stack (a block of empty slots),
   // so popping needs no "is this group active" logic at all
   const uint32_t stack_pop = stack + (grp - G) * 4u;
-  const uint32_t null_link = p.tree.null_link;
+  const uint32_t null_link = QUANT ? p.tree.qnull_link : p.tree.null_link;
   if (lane < G)
-    sts_u32(warp_mem + lane * 4u, null_link);
+    sts_u32(stack - G * 4u + lane * 4u, null_link);
   __syncwarp();
 
-  const unsigned char* lane_blocks = opaque(p.tree.blocks + slot * 16); // this lane's element of a row
-  const uint32_t leaf_link_begin = p.tree.leaf_link_begin;
+  // this lane's element of a row
+  const unsigned char* lane_blocks = opaque((QUANT ? p.tree.qblocks : p.tree.blocks) + slot * 16);
+  // QUANT: the float record behind a leaf slot, relative to the lane's quantised-image pointer
+  const long long leaf_delta = QUANT ? (long long)(p.tree.leaf_blocks - p.tree.qblocks) : 0ll;
+  const uint32_t leaf_link_begin = QUANT ? p.tree.qleaf_link_begin : p.tree.leaf_link_begin;
   const S* __restrict__ queries = static_cast<const S*>(p.queries);
 
   unsigned long long visits_int = 0, visits_leaf = 0, steps = 0;
@@ -104,6 +115,14 @@ box_traverse_kernel(const BoxLaunch p)
         qhi[d] = __ldg(queries + qi * (2 * D) + D + d);
       }
 
+      uint32_t qb[3] = { 0u, 0u, 0u }; // the query on the quantisation grid
+      if constexpr (QUANT)
+      {
+        const float glo[3] = { p.tree.qlo[0], p.tree.qlo[1], p.tree.qlo[2] };
+        const float gscale[3] = { p.tree.qscale[0], p.tree.qscale[1], p.tree.qscale[2] };
+        quant_query(qlo, qhi, glo, gscale, qb);
+      }
+
       unsigned long long out_base = 0;
       uint32_t expect = 0;
       bool buffered = (PASS == PASS_STASH);
@@ -128,24 +147,34 @@ box_traverse_kernel(const BoxLaunch p)
 
         const bool is_leaf = node >= leaf_link_begin;
         uint32_t link;
-        S lo[D], hi[D];
-        load_entry<S, D, W, BOXKEY>(lane_blocks + (unsigned long long)node * 16u, slot, is_leaf, lo, hi, link);
-        bool hit = link != RT_INVALID_ID;
-#pragma unroll
-        for (int d = 0; d < D; ++d)
+        bool hit;
+        if constexpr (QUANT)
         {
-          if (BOXKEY && CONTAINS)
+          const uint4 r = __ldg(reinterpret_cast<const uint4*>(lane_blocks + (unsigned long long)node * 16u));
+          link = r.w;
+          hit = quant_pass(r, qb); // empty slots never pass
+        }
+        else
+        {
+          S lo[D], hi[D];
+          load_entry<S, D, W, BOXKEY>(lane_blocks + (unsigned long long)node * 16u, slot, is_leaf, lo, hi, link);
+          hit = link != RT_INVALID_ID;
+#pragma unroll
+          for (int d = 0; d < D; ++d)
           {
-            // leaf: key box inside the query box; internal: closed overlap
-            const S a = is_leaf ? lo[d] : hi[d];
-            const S b = is_leaf ? hi[d] : lo[d];
-            hit = hit && !(a < qlo[d]) && !(b > qhi[d]);
-          }
-          else
-          {
-            // closed overlap; for a point key (lo == hi) this IS the reference's
-            // is_inside: !(p < qmin) && !(p > qmax) per axis
-            hit = hit && !(hi[d] < qlo[d]) && !(lo[d] > qhi[d]);
+            if (BOXKEY && CONTAINS)
+            {
+              // leaf: key box inside the query box; internal: closed overlap
+              const S a = is_leaf ? lo[d] : hi[d];
+              const S b = is_leaf ? hi[d] : lo[d];
+              hit = hit && !(a < qlo[d]) && !(b > qhi[d]);
+            }
+            else
+            {
+              // closed overlap; for a point key (lo == hi) this IS the reference's
+              // is_inside: !(p < qmin) && !(p > qmax) per axis
+              hit = hit && !(hi[d] < qlo[d]) && !(lo[d] > qhi[d]);
+            }
           }
         }
 
@@ -168,11 +197,26 @@ box_traverse_kernel(const BoxLaunch p)
         // leaf entries that satisfy the predicate
         if (m_leaf != 0)
         {
+          uint32_t m_hits = m_leaf;
+          bool leaf_hit = hit && is_leaf;
+          if constexpr (QUANT)
+          {
+            // candidates of the quantised test: the reference's exact test on the float record
+            if (leaf_hit)
+            {
+              const uint4 e = __ldg(reinterpret_cast<const uint4*>(
+                  lane_blocks + leaf_delta + (unsigned long long)(node - leaf_link_begin) * 16u));
+              const float x = __uint_as_float(e.x), y = __uint_as_float(e.y), z = __uint_as_float(e.z);
+              leaf_hit = !(x < qlo[0]) && !(x > qhi[0]) && !(y < qlo[1]) && !(y > qhi[1]) && !(z < qlo[2])
+                         && !(z > qhi[2]);
+            }
+            m_hits = __ballot_sync(0xFFFFFFFFu, leaf_hit);
+          }
           if (PASS == PASS_STASH || PASS == PASS_WRITE)
           {
-            if (hit && is_leaf)
+            if (leaf_hit)
             {
-              const uint32_t at = count + __popc(m_leaf & lt_mask);
+              const uint32_t at = count + __popc(m_hits & lt_mask);
               if (buffered)
               {
                 if (at < HIT_BUF)
@@ -184,7 +228,7 @@ box_traverse_kernel(const BoxLaunch p)
               }
             }
           }
-          count += __popc(m_leaf);
+          count += __popc(m_hits);
         }
         __syncwarp();
       }
@@ -264,12 +308,19 @@ box_traverse_kernel(const BoxLaunch p)
     atomicAdd(p.visit_stats + 1, visits_leaf);
     atomicAdd(p.visit_stats + 3, steps);
   }
+#undef hitbuf
 }
 
-template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS>
+template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS, bool QUANT = false>
 cudaError_t launch_box_pass(const BoxLaunch& p)
 {
-  auto kernel = box_traverse_kernel<S, D, W, BOXKEY, CONTAINS, PASS>;
+  constexpr bool CAN_QUANT = std::is_same<S, float>::value && D == 3 && W == 8 && !BOXKEY && PASS != PASS_COUNT_STATS;
+  if constexpr (CAN_QUANT && !QUANT)
+  {
+    if (p.tree.qblocks != nullptr)
+      return launch_box_pass<S, D, W, BOXKEY, CONTAINS, PASS, true>(p);
+  }
+  auto kernel = box_traverse_kernel<S, D, W, BOXKEY, CONTAINS, PASS, QUANT>;
   const size_t smem = traverse_smem_bytes(p.tree.num_levels, W);
   cudaError_t err = cudaSuccess;
   if (smem > 48 * 1024)

@@ -49,13 +49,13 @@ ray_traverse_kernel(const RayLaunch p)
 
   // per warp: G words holding the null node, the stack, the hit buffer (see rt_traverse_box.cuh)
   const uint32_t stack_cap = 32u * p.tree.num_levels;
-  const uint32_t warp_mem = smem_addr(smem + warp * (G + stack_cap + HIT_BUF));
-  const uint32_t stack = warp_mem + G * 4u;
-  const uint32_t hitbuf = stack + stack_cap * 4u;
+  const uint32_t warp_mem = smem_addr(smem + warp * (HIT_BUF + G + stack_cap));
+  const uint32_t stack = warp_mem + (HIT_BUF + G) * 4u;
+  const uint32_t hitbuf = warp_mem;
   const uint32_t stack_pop = stack + (grp - G) * 4u; // group g pops stack index sp - G + g
   const uint32_t null_link = p.tree.null_link;
   if (lane < G)
-    sts_u32(warp_mem + lane * 4u, null_link);
+    sts_u32(stack - G * 4u + lane * 4u, null_link);
   __syncwarp();
 
   const unsigned char* lane_blocks = opaque(p.tree.blocks + slot * 16); // this lane's element of a row

@@ -279,3 +279,76 @@ def test_pipelined_call_equals_single_batch(rtb, flags):
             assert np.array_equal(single[0], ref[0])
         else:
             assert csr_equal(single, ref)
+
+
+def _boundary_queries(pts, rng, n):
+    """query boxes whose faces pass exactly through data points (closed intervals: those points are hits)"""
+    a = pts[rng.integers(0, len(pts), n)]
+    b = pts[rng.integers(0, len(pts), n)]
+    return np.stack([np.minimum(a, b), np.maximum(a, b)], axis=1).astype(np.float32)
+
+
+QUANT_CASES = ["uniform", "flat_axis", "huge_range", "tiny_range", "negative_denormal", "single_leaf",
+               "single_leaf_extreme", "duplicates"]
+
+
+@pytest.mark.parametrize("case", QUANT_CASES)
+def test_quantised_image_gives_the_exact_hit_sets(rtb, case):
+    """3-D float32 point trees are traversed on a quantised image (conservative 15-bit bounds, leaf
+    candidates confirmed on the float records): hit lists must equal the float-block path and the
+    reference's search() bit for bit, also where quantisation is at its worst"""
+    rng = np.random.default_rng(700 + QUANT_CASES.index(case))
+    n = 40000
+    pts = rng.random((n, 3)).astype(np.float32)
+    if case == "flat_axis":
+        pts[:, 1] = np.float32(0.25)                       # zero extent on one axis
+    elif case == "huge_range":
+        # (the reference's insert segfaults once bound areas overflow float32, i.e. beyond ~7e12 per
+        # axis -- stay below; an overflowing extent is exercised by single_leaf_extreme)
+        pts = (pts * np.float32(2e12) - np.float32(1e12)).astype(np.float32)
+    elif case == "tiny_range":
+        pts = (np.float32(1000.0) + pts * np.float32(1e-3)).astype(np.float32)   # few ulps between keys
+    elif case == "negative_denormal":
+        pts = (pts - np.float32(0.5)).astype(np.float32)
+        pts[:200] *= np.float32(1e-42)                     # denormals around zero
+    elif case == "single_leaf":
+        pts = pts[:6]
+    elif case == "single_leaf_extreme":
+        pts = pts[:6]
+        pts[0] = [3e38, -3e38, 3e38]                       # root extent overflows to +inf: scale 0 on every axis
+        pts[1] = [-3e38, 3e38, -3e38]
+    elif case == "duplicates":
+        pts = pts[rng.integers(0, 50, n)]                  # 50 distinct points, long equal runs
+    span = pts.max(axis=0) - pts.min(axis=0)
+    with np.errstate(over="ignore", invalid="ignore"):
+        c = pts[rng.integers(0, len(pts), 3000)]
+        h = (np.where(np.isfinite(span), span, np.float32(1e30)) * np.float32(0.02)).astype(np.float32)
+        q = np.concatenate([
+            np.stack([c - h, c + h], axis=1).astype(np.float32),
+            _boundary_queries(pts, rng, 3000),
+            np.stack([c, c], axis=1),                                     # zero-size boxes on data points
+            np.stack([c + h, c - h], axis=1).astype(np.float32)[:200],    # inverted
+        ])
+    special = np.zeros((8, 2, 3), np.float32)
+    special[0] = [[-np.inf] * 3, [np.inf] * 3]
+    special[1] = [[np.nan] * 3, [np.nan] * 3]
+    special[2] = [pts.min(axis=0), pts.max(axis=0)]                       # exactly the root box
+    special[3] = [pts.max(axis=0), [np.inf] * 3]                          # touches the root box in one corner
+    special[4] = [[-np.inf] * 3, pts.min(axis=0)]
+    special[5] = [[np.nan, -np.inf, pts[0, 2]], [np.inf, np.nan, pts[0, 2]]]
+    special[6] = [pts.max(axis=0) + np.float32(1.0), pts.max(axis=0) + np.float32(2.0)]   # outside
+    special[7] = [[-3e38] * 3, [3e38] * 3]
+    q = np.concatenate([q, special])
+    want = O.RefTree(4).insert(pts).search_boxes(q)
+    assert want[1].size > 0
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+        for flags in (0, rtb.RT_NO_REORDER, rtb.RT_UNSORTED, rtb.RT_COUNT_ONLY):
+            got = {}
+            for quantised in (1, 0):
+                tree.set_option(rtb.RT_OPT_QUANTISED, quantised)
+                got[quantised] = tree.query_boxes(q, flags=flags)
+            assert np.array_equal(got[1][0], got[0][0]) and np.array_equal(got[1][0], want[0])
+            if flags == rtb.RT_UNSORTED:
+                assert np.array_equal(sort_segments(*got[1]), want[1]) and np.array_equal(sort_segments(*got[0]), want[1])
+            elif flags != rtb.RT_COUNT_ONLY:
+                assert np.array_equal(got[1][1], want[1]) and np.array_equal(got[0][1], want[1])
