@@ -414,4 +414,19 @@ extern "C"
     return static_cast<rt::device_tree_t*>(image)->bfs_to_dfs.data();
   }
   void rtb_device_tree_free(void* image) { delete static_cast<rt::device_tree_t*>(image); }
+  // on-disk form of the image (RTree/device_layout.hpp: save_device_tree / load_device_tree)
+  int rtb_device_tree_save(void* image, const char* path)
+  {
+    return guarded(
+        [&]() -> int
+        {
+          rt::save_device_tree(*static_cast<rt::device_tree_t*>(image), path);
+          return 0;
+        },
+        -1);
+  }
+  void* rtb_device_tree_load(const char* path)
+  {
+    return guarded([&]() -> void* { return new rt::device_tree_t(rt::load_device_tree(path)); }, (void*)nullptr);
+  }
 }

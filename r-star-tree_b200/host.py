@@ -76,6 +76,10 @@ def lib():
         L.rtb_device_tree_bfs_to_dfs.restype = C.POINTER(u32)
         L.rtb_device_tree_bfs_to_dfs.argtypes = [vp]
         L.rtb_device_tree_free.argtypes = [vp]
+        L.rtb_device_tree_save.restype = C.c_int
+        L.rtb_device_tree_save.argtypes = [vp, C.c_char_p]
+        L.rtb_device_tree_load.restype = vp
+        L.rtb_device_tree_load.argtypes = [C.c_char_p]
         _lib = L
     return _lib
 
@@ -122,6 +126,19 @@ class DeviceImage:
     def upload(self, device=0):
         """rt_upload(): copy the image to a GPU, returns a capi.DeviceTree."""
         return capi.DeviceTree(self.desc, device, keepalive=self)
+
+    def save(self, path):
+        """save_device_tree(): write the image to one file (header + tables + blocks, checksummed)."""
+        if lib().rtb_device_tree_save(self._h, os.fsencode(path)) != 0:
+            raise RuntimeError("save_device_tree failed: " + _err())
+
+    @staticmethod
+    def load(path):
+        """load_device_tree(): read an image back; raises if the file is truncated or corrupted."""
+        h = lib().rtb_device_tree_load(os.fsencode(path))
+        if not h:
+            raise RuntimeError("load_device_tree failed: " + _err())
+        return DeviceImage(h)
 
     @staticmethod
     def from_flat(kind, leaf_level, nodes, bounds, children, data, ids_from_mapped=True):

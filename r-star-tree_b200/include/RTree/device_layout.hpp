@@ -22,11 +22,13 @@
 #pragma once
 
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
 #include <stdexcept>
+#include <string>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -328,6 +330,156 @@ device_tree_t flatten_device(FlattenResult const& flat, id_source ids = id_sourc
       *word_at(block, words, c, D * SW) = link;
     }
   }
+  return out;
+}
+
+// ---- on-disk form of the image --------------------------------------------------------------
+// A tree built once on the CPU (minutes for 10^8 keys) can be saved and reloaded without the
+// insert loop.  Little-endian, one file:
+//   header (128 bytes)  magic "RTB200IM", format version, the rt_tree_desc scalars, section sizes,
+//                       FNV-1a-64 checksum of everything after the header
+//   level_node_begin    (num_levels + 1) x u32
+//   bfs_to_dfs          num_nodes x u32
+//   padding to a multiple of 256 bytes, then the blocks exactly as rt_upload() takes them
+namespace detail
+{
+struct image_file_header
+{
+  char magic[8];
+  std::uint32_t format_version;
+  std::uint32_t header_bytes;
+  std::uint32_t abi_version, dim, scalar, width, max_entries, key_kind, leaf_level, num_levels, num_nodes,
+      num_values, internal_stride, leaf_stride;
+  std::uint64_t leaf_offset;
+  std::uint64_t blocks_bytes;
+  std::uint64_t blocks_file_offset;
+  std::uint64_t checksum;
+  unsigned char reserved[128 - 8 - 4 * 14 - 8 * 4];
+};
+static_assert(sizeof(image_file_header) == 128, "image_file_header layout");
+
+constexpr std::uint32_t IMAGE_FORMAT_VERSION = 1;
+
+inline std::uint64_t fnv1a64(const void* data, std::size_t n, std::uint64_t h = 0xcbf29ce484222325ull)
+{
+  // 8 bytes at a time (a byte-wise FNV over gigabytes would dominate the load)
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  std::size_t i = 0;
+  for (; i + 8 <= n; i += 8)
+  {
+    std::uint64_t w;
+    std::memcpy(&w, p + i, 8);
+    h = (h ^ w) * 0x100000001b3ull;
+  }
+  for (; i < n; ++i)
+    h = (h ^ p[i]) * 0x100000001b3ull;
+  return h;
+}
+
+struct file_closer
+{
+  std::FILE* f;
+  ~file_closer()
+  {
+    if (f)
+      std::fclose(f);
+  }
+};
+} // namespace detail
+
+/// write `image` to `path`; throws std::runtime_error on I/O failure
+inline void save_device_tree(device_tree_t const& image, std::string const& path)
+{
+  detail::image_file_header h;
+  std::memset(&h, 0, sizeof h);
+  std::memcpy(h.magic, "RTB200IM", 8);
+  h.format_version = detail::IMAGE_FORMAT_VERSION;
+  h.header_bytes = sizeof h;
+  const rt_tree_desc d = image.desc();
+  h.abi_version = d.abi_version, h.dim = d.dim, h.scalar = d.scalar, h.width = d.width;
+  h.max_entries = d.max_entries, h.key_kind = d.key_kind, h.leaf_level = d.leaf_level;
+  h.num_levels = d.num_levels, h.num_nodes = d.num_nodes, h.num_values = d.num_values;
+  h.internal_stride = d.internal_stride, h.leaf_stride = d.leaf_stride;
+  h.leaf_offset = d.leaf_offset;
+  h.blocks_bytes = d.blocks_bytes;
+  if (image.level_node_begin.size() != std::size_t(h.num_levels) + 1 || image.bfs_to_dfs.size() != h.num_nodes)
+    throw std::runtime_error("save_device_tree: inconsistent image");
+  const std::uint64_t tables = 4ull * (image.level_node_begin.size() + image.bfs_to_dfs.size());
+  h.blocks_file_offset = (sizeof h + tables + 255) / 256 * 256;
+  std::vector<unsigned char> pad(std::size_t(h.blocks_file_offset - sizeof h - tables), 0);
+  std::uint64_t sum = detail::fnv1a64(image.level_node_begin.data(), 4 * image.level_node_begin.size());
+  sum = detail::fnv1a64(image.bfs_to_dfs.data(), 4 * image.bfs_to_dfs.size(), sum);
+  sum = detail::fnv1a64(pad.data(), pad.size(), sum);
+  sum = detail::fnv1a64(image.blocks.data(), image.blocks.size(), sum);
+  h.checksum = sum;
+
+  detail::file_closer file { std::fopen(path.c_str(), "wb") };
+  if (file.f == nullptr)
+    throw std::runtime_error("save_device_tree: cannot open " + path);
+  auto put = [&](const void* p, std::size_t n)
+  {
+    if (n && std::fwrite(p, 1, n, file.f) != n)
+      throw std::runtime_error("save_device_tree: short write to " + path);
+  };
+  put(&h, sizeof h);
+  put(image.level_node_begin.data(), 4 * image.level_node_begin.size());
+  put(image.bfs_to_dfs.data(), 4 * image.bfs_to_dfs.size());
+  put(pad.data(), pad.size());
+  put(image.blocks.data(), image.blocks.size());
+  if (std::fflush(file.f) != 0)
+    throw std::runtime_error("save_device_tree: flush failed for " + path);
+}
+
+/// read an image written by save_device_tree(); throws std::runtime_error if the file is not a
+/// complete, uncorrupted image of a format this header understands
+inline device_tree_t load_device_tree(std::string const& path)
+{
+  detail::file_closer file { std::fopen(path.c_str(), "rb") };
+  if (file.f == nullptr)
+    throw std::runtime_error("load_device_tree: cannot open " + path);
+  auto get = [&](void* p, std::size_t n, const char* what)
+  {
+    if (n && std::fread(p, 1, n, file.f) != n)
+      throw std::runtime_error(std::string("load_device_tree: file truncated in ") + what);
+  };
+  detail::image_file_header h;
+  get(&h, sizeof h, "header");
+  if (std::memcmp(h.magic, "RTB200IM", 8) != 0)
+    throw std::runtime_error("load_device_tree: not an rtree-b200 image (bad magic)");
+  if (h.format_version != detail::IMAGE_FORMAT_VERSION || h.header_bytes != sizeof h)
+    throw std::runtime_error("load_device_tree: unsupported image format version");
+  if (h.abi_version != RT_ABI_VERSION)
+    throw std::runtime_error("load_device_tree: image written for another ABI version");
+  if (h.num_levels != h.leaf_level + 1 || h.num_levels > 64 || h.num_nodes == 0 || h.dim < 1 || h.dim > 8
+      || h.blocks_bytes > (std::uint64_t(1) << 40))
+    throw std::runtime_error("load_device_tree: implausible header");
+  const std::uint64_t tables = 4ull * (std::uint64_t(h.num_levels) + 1 + h.num_nodes);
+  if (h.blocks_file_offset != (sizeof h + tables + 255) / 256 * 256)
+    throw std::runtime_error("load_device_tree: implausible header");
+
+  device_tree_t out;
+  out.dim = h.dim, out.scalar = h.scalar, out.width = h.width, out.max_entries = h.max_entries;
+  out.key_kind = h.key_kind, out.leaf_level = h.leaf_level, out.num_values = h.num_values;
+  out.internal_stride = h.internal_stride, out.leaf_stride = h.leaf_stride, out.leaf_offset = h.leaf_offset;
+  out.level_node_begin.resize(std::size_t(h.num_levels) + 1);
+  out.bfs_to_dfs.resize(h.num_nodes);
+  get(out.level_node_begin.data(), 4 * out.level_node_begin.size(), "level table");
+  get(out.bfs_to_dfs.data(), 4 * out.bfs_to_dfs.size(), "node table");
+  std::vector<unsigned char> pad(std::size_t(h.blocks_file_offset - sizeof h - tables), 0);
+  get(pad.data(), pad.size(), "padding");
+  out.blocks = detail::aligned_bytes(h.blocks_bytes);
+  get(out.blocks.data(), out.blocks.size(), "blocks");
+  unsigned char extra;
+  if (std::fread(&extra, 1, 1, file.f) != 0)
+    throw std::runtime_error("load_device_tree: trailing bytes after the blocks");
+  std::uint64_t sum = detail::fnv1a64(out.level_node_begin.data(), 4 * out.level_node_begin.size());
+  sum = detail::fnv1a64(out.bfs_to_dfs.data(), 4 * out.bfs_to_dfs.size(), sum);
+  sum = detail::fnv1a64(pad.data(), pad.size(), sum);
+  sum = detail::fnv1a64(out.blocks.data(), out.blocks.size(), sum);
+  if (sum != h.checksum)
+    throw std::runtime_error("load_device_tree: checksum mismatch (corrupted image)");
+  if (out.level_node_begin.back() != h.num_nodes)
+    throw std::runtime_error("load_device_tree: level table inconsistent with the header");
   return out;
 }
 

@@ -352,3 +352,14 @@ def test_quantised_image_gives_the_exact_hit_sets(rtb, case):
                 assert np.array_equal(sort_segments(*got[1]), want[1]) and np.array_equal(sort_segments(*got[0]), want[1])
             elif flags != rtb.RT_COUNT_ONLY:
                 assert np.array_equal(got[1][1], want[1]) and np.array_equal(got[0][1], want[1])
+
+
+def test_reloaded_image_answers_like_the_original(rtb, tmp_path):
+    """an image saved with save_device_tree and loaded back uploads and answers identically"""
+    pts = rtb.workloads.uniform_points(30000, seed=21)
+    q = rtb.workloads.cube_queries(5000, 30000, seed=22)
+    image = rtb.RTree(4).insert(pts).flatten_device()
+    path = str(tmp_path / "tree.rtb")
+    image.save(path)
+    with image.upload(0) as a, rtb.DeviceImage.load(path).upload(0) as b:
+        assert csr_equal(a.query_boxes(q), b.query_boxes(q))

@@ -217,3 +217,40 @@ int main()
     for byte in image.blocks().tobytes():
         h = ((h ^ byte) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
     assert h == fnv
+
+
+def test_device_image_file_round_trip_and_corruption(rtb, tmp_path):
+    """save_device_tree / load_device_tree (RTree/device_layout.hpp): the reloaded image is the saved
+    one byte for byte; truncated, corrupted or foreign files are refused"""
+    rng = np.random.default_rng(5)
+    for kind, keys in ((4, rng.random((5000, 3)).astype(np.float32)),
+                       (2, rng.random((700, 2))),
+                       (5, np.sort(rng.random((900, 2, 3)).astype(np.float32), axis=1)),
+                       (4, rng.random((3, 3)).astype(np.float32))):
+        image = rtb.RTree(kind).insert(keys).flatten_device()
+        path = str(tmp_path / ("tree%d_%d.rtb" % (kind, len(keys))))
+        image.save(path)
+        back = rtb.DeviceImage.load(path)
+        for name, _ in rtb.capi.RtTreeDesc._fields_:
+            if name not in ("blocks", "level_node_begin", "reserved"):
+                assert getattr(back.desc, name) == getattr(image.desc, name), name
+        assert np.array_equal(back.level_node_begin, image.level_node_begin)
+        assert np.array_equal(back.bfs_to_dfs, image.bfs_to_dfs)
+        assert np.array_equal(back.blocks(), image.blocks())
+    raw = bytearray(open(path, "rb").read())
+    cases = {"truncated": raw[:len(raw) - 7], "trailing": raw + b"x", "magic": b"NOTANIMG" + raw[8:],
+             "header_only": raw[:128], "empty": b""}
+    flipped = bytearray(raw)
+    flipped[-1] ^= 0x40                      # one bit in the blocks
+    cases["bitflip"] = flipped
+    version = bytearray(raw)
+    version[8] = 99
+    cases["version"] = version
+    for name, data in cases.items():
+        bad = str(tmp_path / (name + ".rtb"))
+        with open(bad, "wb") as f:
+            f.write(data)
+        with pytest.raises(RuntimeError):
+            rtb.DeviceImage.load(bad)
+    with pytest.raises(RuntimeError):
+        rtb.DeviceImage.load(str(tmp_path / "does_not_exist.rtb"))
