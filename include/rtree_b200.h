@@ -17,6 +17,7 @@
  *   rt_query_rays    <- the same search() driven by a stateful slab-test filter
  *                       (legal per reference rtree.hpp:1145); all-hits, closest-hit,
  *                       any-hit (functor returning true, reference rtree.hpp:994-997)
+ *   rt_query_knn     <- the same search() with a distance-pruning filter and a k-best functor
  *   rt_free          <- releases the device copy
  *
  * Plain C, plain pointers and sizes; no exceptions cross the boundary.  Every call
@@ -204,6 +205,24 @@ int rt_query_boxes(rt_tree* tree, const void* boxes, uint64_t n, uint32_t mode,
  * every consumer sees the same bits), tmax; tmin is 0.  3-D f32 trees only.            */
 int rt_query_rays(rt_tree* tree, const float* rays, uint64_t n, uint32_t mode,
                   uint32_t flags, rt_ray_result* out);
+
+/* k nearest neighbours: RTree::search() driven by a pruning filter and a k-best
+ * functor, defined in oracle/knn.h.  ids[q*k .. q*k+k) / dist2[...] are the k keys nearest to point
+ * q, ascending by (dist2, id); dist2 is the squared Euclidean distance to the key (to the key's box
+ * for box keys), float32; when the tree holds fewer than k keys the tail is (RT_INVALID_ID, +inf).  */
+typedef struct rt_knn_result
+{
+  uint64_t n_queries;
+  uint32_t k;
+  uint32_t memory;       /* RT_MEM_HOST (pinned) | RT_MEM_DEVICE */
+  const uint32_t* ids;   /* [n_queries][k] */
+  const float* dist2;    /* [n_queries][k] */
+} rt_knn_result;
+
+/* points: [n][dim] float32.  float32 trees with dim 2 or 3 and 8-wide blocks; 1 <= k <= 32.
+ * Flags: RT_QUERIES_ON_DEVICE, RT_RESULT_ON_DEVICE, RT_NO_REORDER, RT_COLLECT_VISITS.      */
+int rt_query_knn(rt_tree* tree, const float* points, uint64_t n, uint32_t k, uint32_t flags,
+                 rt_knn_result* out);
 
 /* Release the handle and every buffer it handed out.  NULL is a no-op.                */
 void rt_free(rt_tree* tree);

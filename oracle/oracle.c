@@ -29,6 +29,8 @@
 
 #include "oracle.h"
 #include "slab.h"
+#include "knn.h"
+#include <math.h>
 
 #define ORACLE_MAX_DIM 16
 
@@ -314,3 +316,151 @@ int64_t oracle_brute_rays(const float* key_boxes, uint64_t n_keys,
 }
 
 void oracle_free(void* p) { free(p); }
+
+/* ---- kNN (f32) ------------------------------------------------------------------ */
+typedef struct
+{
+  float d2;
+  uint32_t id;
+} knn_pair;
+
+typedef struct
+{
+  const oracle_flat* f;
+  int key_is_box;
+  const float* q;
+  uint32_t k, have;
+  knn_pair* best; /* [k], unordered; worst tracked below */
+  uint32_t worst; /* index of the worst pair once have == k */
+  uint64_t v_int, v_leaf;
+} knnctx;
+
+static void knn_find_worst(knnctx* c)
+{
+  uint32_t i, w = 0;
+  for (i = 1; i < c->k; ++i)
+    if (rt_knn_less(c->best[w].d2, c->best[w].id, c->best[i].d2, c->best[i].id))
+      w = i;
+  c->worst = w;
+}
+static void knn_offer(knnctx* c, float d2, uint32_t id)
+{
+  if (c->have < c->k)
+  {
+    c->best[c->have].d2 = d2;
+    c->best[c->have].id = id;
+    if (++c->have == c->k)
+      knn_find_worst(c);
+    return;
+  }
+  if (rt_knn_less(d2, id, c->best[c->worst].d2, c->best[c->worst].id))
+  {
+    c->best[c->worst].d2 = d2;
+    c->best[c->worst].id = id;
+    knn_find_worst(c);
+  }
+}
+static float knn_bound(const knnctx* c)
+{
+  return c->have < c->k ? INFINITY : c->best[c->worst].d2;
+}
+static void walk_knn(knnctx* c, uint32_t node, uint32_t level)
+{
+  const oracle_flat* f = c->f;
+  const uint32_t off = f->nodes[3 * node], size = f->nodes[3 * node + 1], dim = f->dim;
+  const float* b = (const float*)f->bounds;
+  uint32_t i;
+  if (level == f->leaf_level)
+  {
+    c->v_leaf++;
+    for (i = 0; i < size; ++i)
+    {
+      const float* lo = b + (uint64_t)(off + i) * 2 * dim;
+      knn_offer(c, rt_knn_dist2(lo, lo + dim, c->q, (int)dim), f->data[f->children[off + i]]);
+    }
+    return;
+  }
+  c->v_int++;
+  for (i = 0; i < size; ++i)
+  {
+    const float* lo = b + (uint64_t)(off + i) * 2 * dim;
+    if (rt_knn_dist2(lo, lo + dim, c->q, (int)dim) <= knn_bound(c))
+      walk_knn(c, f->children[off + i], level + 1);
+  }
+}
+static int cmp_knn(const void* a, const void* b)
+{
+  const knn_pair* x = (const knn_pair*)a;
+  const knn_pair* y = (const knn_pair*)b;
+  if (x->d2 < y->d2)
+    return -1;
+  if (x->d2 > y->d2)
+    return 1;
+  return (x->id > y->id) - (x->id < y->id);
+}
+static void knn_emit(knn_pair* best, uint32_t have, uint32_t k, uint32_t* ids_out, float* d2_out)
+{
+  uint32_t i;
+  qsort(best, have, sizeof(knn_pair), cmp_knn);
+  for (i = 0; i < k; ++i)
+  {
+    ids_out[i] = i < have ? best[i].id : 0xFFFFFFFFu;
+    d2_out[i] = i < have ? best[i].d2 : INFINITY;
+  }
+}
+
+int64_t oracle_query_knn(const oracle_flat* f, int key_is_box, const float* points, uint64_t n, uint32_t k,
+                         uint32_t* ids_out, float* d2_out, uint64_t* visits)
+{
+  knnctx c;
+  uint64_t i;
+  if (f->scalar != ORACLE_F32 || f->dim == 0 || f->dim > ORACLE_MAX_DIM || k == 0)
+    return -1;
+  memset(&c, 0, sizeof c);
+  c.f = f;
+  c.key_is_box = key_is_box;
+  c.k = k;
+  c.best = (knn_pair*)malloc(sizeof(knn_pair) * k);
+  for (i = 0; i < n; ++i)
+  {
+    c.q = points + i * f->dim;
+    c.have = 0;
+    if (f->n_nodes > 0)
+      walk_knn(&c, f->root, 0);
+    knn_emit(c.best, c.have, k, ids_out + i * k, d2_out + i * k);
+  }
+  if (visits)
+  {
+    visits[0] = c.v_int;
+    visits[1] = c.v_leaf;
+  }
+  free(c.best);
+  return 0;
+}
+
+int64_t oracle_brute_knn(const float* keys, uint64_t n_keys, int key_is_box, const uint32_t* key_ids,
+                         uint32_t dim, const float* points, uint64_t n, uint32_t k, uint32_t* ids_out,
+                         float* d2_out)
+{
+  knnctx c;
+  uint64_t i, j;
+  const uint64_t stride = (uint64_t)dim * (key_is_box ? 2 : 1);
+  if (dim == 0 || dim > ORACLE_MAX_DIM || k == 0)
+    return -1;
+  memset(&c, 0, sizeof c);
+  c.k = k;
+  c.best = (knn_pair*)malloc(sizeof(knn_pair) * k);
+  for (i = 0; i < n; ++i)
+  {
+    c.have = 0;
+    for (j = 0; j < n_keys; ++j)
+    {
+      const float* lo = keys + j * stride;
+      const float* hi = key_is_box ? lo + dim : lo;
+      knn_offer(&c, rt_knn_dist2(lo, hi, points + i * dim, (int)dim), key_ids ? key_ids[j] : (uint32_t)j);
+    }
+    knn_emit(c.best, c.have, k, ids_out + i * k, d2_out + i * k);
+  }
+  free(c.best);
+  return 0;
+}

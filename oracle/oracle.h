@@ -44,6 +44,14 @@ int64_t oracle_brute_rays(const float* key_boxes, uint64_t n_keys,
                           const uint32_t* key_ids, const float* rays, uint64_t n,
                           int mode, uint64_t* offsets, uint32_t** ids,
                           float* t_out, uint32_t* id_out, uint8_t* any_out);
+/* kNN (oracle/knn.h), float32 trees: points [n][dim]; ids_out / d2_out: [n][k] ascending by (d2, id),
+ * padded with (0xFFFFFFFF, +inf).  visits (nullable): [2] internal / leaf node visits of the
+ * depth-first traversal in child order.  Returns 0, or -1 for an unsupported tree. */
+int64_t oracle_query_knn(const oracle_flat* f, int key_is_box, const float* points, uint64_t n, uint32_t k,
+                         uint32_t* ids_out, float* d2_out, uint64_t* visits);
+int64_t oracle_brute_knn(const float* keys, uint64_t n_keys, int key_is_box, const uint32_t* key_ids,
+                         uint32_t dim, const float* points, uint64_t n, uint32_t k, uint32_t* ids_out,
+                         float* d2_out);
 void oracle_free(void* p);
 
 #ifdef __cplusplus

@@ -36,6 +36,7 @@
 #endif
 
 #include "slab.h"
+#include "knn.h"
 
 namespace er = eh::rtree;
 
@@ -88,6 +89,8 @@ struct ITree
                               int threads, uint64_t* offsets, uint32_t** ids,
                               float* t_out, uint32_t* id_out, uint8_t* any_out,
                               double* seconds) const = 0;
+  virtual int64_t search_knn(const float* points, uint64_t n, uint32_t k, int threads,
+                             uint32_t* ids_out, float* d2_out, double* seconds) const = 0;
 };
 
 // ---- geometry adapters: how a C array row becomes a reference key / box ------
@@ -450,6 +453,86 @@ struct TreeImpl : ITree
     return rays_impl(rays, n, mode, threads, offsets, ids, t_out, id_out,
                      any_out, seconds);
   }
+
+  // kNN (oracle/knn.h): the reference's search() with a pruning filter and a k-best functor ----
+  template <typename SS = S>
+  typename std::enable_if<std::is_same<SS, float>::value, int64_t>::type
+  knn_impl(const float* points, uint64_t n, uint32_t k, int threads, uint32_t* ids_out, float* d2_out,
+           double* seconds) const
+  {
+#ifdef _OPENMP
+    if (threads <= 0)
+      threads = omp_get_max_threads();
+#else
+    threads = 1;
+#endif
+    auto t0c = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
+    for (int64_t i = 0; i < (int64_t)n; ++i)
+    {
+      const float* q = points + i * D;
+      std::vector<std::pair<float, uint32_t>> best; // unordered; `worst` valid once full
+      best.reserve(k);
+      size_t worst = 0;
+      auto find_worst = [&]()
+      {
+        worst = 0;
+        for (size_t j = 1; j < best.size(); ++j)
+          if (rt_knn_less(best[worst].first, best[worst].second, best[j].first, best[j].second))
+            worst = j;
+      };
+      auto bound = [&]() -> float { return best.size() < k ? INFINITY : best[worst].first; };
+      auto filter = [&](box const& b) -> int
+      {
+        float lo[D], hi[D];
+        for (unsigned d = 0; d < D; ++d)
+          lo[d] = A::lo(b, d), hi[d] = A::hi(b, d);
+        return rt_knn_dist2(lo, hi, q, (int)D) <= bound() ? 1 : 0; // non-strict: ties survive
+      };
+      auto functor = [&](value_t const& v) -> bool
+      {
+        box kb(v.first);
+        float lo[D], hi[D];
+        for (unsigned d = 0; d < D; ++d)
+          lo[d] = A::lo(kb, d), hi[d] = A::hi(kb, d);
+        const float d2 = rt_knn_dist2(lo, hi, q, (int)D);
+        if (best.size() < k)
+        {
+          best.emplace_back(d2, v.second);
+          if (best.size() == k)
+            find_worst();
+        }
+        else if (rt_knn_less(d2, v.second, best[worst].first, best[worst].second))
+        {
+          best[worst] = { d2, v.second };
+          find_worst();
+        }
+        return false;
+      };
+      tree.search(filter, functor);
+      std::sort(best.begin(), best.end());
+      for (uint32_t j = 0; j < k; ++j)
+      {
+        ids_out[i * k + j] = j < best.size() ? best[j].second : 0xFFFFFFFFu;
+        d2_out[i * k + j] = j < best.size() ? best[j].first : INFINITY;
+      }
+    }
+    auto t1c = std::chrono::steady_clock::now();
+    if (seconds)
+      *seconds = std::chrono::duration<double>(t1c - t0c).count();
+    return 0;
+  }
+  template <typename SS = S>
+  typename std::enable_if<!std::is_same<SS, float>::value, int64_t>::type
+  knn_impl(const float*, uint64_t, uint32_t, int, uint32_t*, float*, double*) const
+  {
+    return -1;
+  }
+  int64_t search_knn(const float* points, uint64_t n, uint32_t k, int threads, uint32_t* ids_out,
+                     float* d2_out, double* seconds) const override
+  {
+    return knn_impl(points, n, k, threads, ids_out, d2_out, seconds);
+  }
 };
 
 ITree* make_tree(int kind)
@@ -517,6 +600,11 @@ extern "C"
     return static_cast<ITree*>(h)->search_rays(rays, n, mode, threads, offsets,
                                                ids, t_out, id_out, any_out,
                                                seconds);
+  }
+  int64_t ref_search_knn(void* h, const float* points, uint64_t n, uint32_t k, int threads,
+                         uint32_t* ids_out, float* d2_out, double* seconds)
+  {
+    return static_cast<ITree*>(h)->search_knn(points, n, k, threads, ids_out, d2_out, seconds);
   }
   void ref_free(void* p) { std::free(p); }
   int ref_max_threads()

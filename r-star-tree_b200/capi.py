@@ -29,7 +29,7 @@ RT_OPT_QUANTISED = 5
 SCALAR_DTYPES = {RT_F32: np.float32, RT_F64: np.float64, RT_I32: np.int32}
 
 # every symbol include/rtree_b200.h declares
-EXPORTS = ["rt_upload", "rt_query_boxes", "rt_query_rays", "rt_free", "rt_set_stream",
+EXPORTS = ["rt_upload", "rt_query_boxes", "rt_query_rays", "rt_query_knn", "rt_free", "rt_set_stream",
            "rt_set_option", "rt_get_stats", "rt_tree_device_blocks", "rt_tree_get_desc", "rt_last_error",
            "rt_abi_version", "rt_device_count"]
 
@@ -60,6 +60,11 @@ class RtRayResult(C.Structure):
     _fields_ = [("n_rays", C.c_uint64), ("n_hit", C.c_uint64), ("hits", RtHits),
                 ("t", C.c_void_p), ("id", C.c_void_p), ("any", C.c_void_p),
                 ("memory", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class RtKnnResult(C.Structure):
+    _fields_ = [("n_queries", C.c_uint64), ("k", C.c_uint32), ("memory", C.c_uint32),
+                ("ids", C.c_void_p), ("dist2", C.c_void_p)]
 
 
 class RtStats(C.Structure):
@@ -99,6 +104,9 @@ def lib():
                                     C.POINTER(RtRayResult)]
         L.rt_free.restype = None
         L.rt_free.argtypes = [C.c_void_p]
+        L.rt_query_knn.restype = C.c_int
+        L.rt_query_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                                   C.POINTER(RtKnnResult)]
         L.rt_set_stream.restype = C.c_int
         L.rt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.rt_set_option.restype = C.c_int
@@ -203,6 +211,19 @@ class DeviceTree:
         offsets = _host_array(out.offsets, out.n_queries + 1, np.uint64)
         ids = _host_array(out.ids, 0 if flags & RT_COUNT_ONLY else out.total, np.uint32)
         return offsets, ids
+
+    def query_knn_raw(self, points_ptr, n, k, flags=0):
+        out = RtKnnResult()
+        _check(lib().rt_query_knn(self._h, C.c_void_p(points_ptr), n, k, flags, C.byref(out)))
+        return out
+
+    def query_knn(self, points, k, flags=0):
+        """points: host array [n][dim] float32 -> (ids[n][k] uint32, dist2[n][k] float32)."""
+        p = np.ascontiguousarray(points, np.float32).reshape(-1, self.dim)
+        flags &= ~(RT_QUERIES_ON_DEVICE | RT_RESULT_ON_DEVICE)
+        out = self.query_knn_raw(p.ctypes.data, len(p), k, flags)
+        return (_host_array(out.ids, len(p) * k, np.uint32).reshape(len(p), k),
+                _host_array(out.dist2, len(p) * k, np.float32).reshape(len(p), k))
 
     def query_rays_raw(self, rays_ptr, n, mode, flags=0):
         out = RtRayResult()

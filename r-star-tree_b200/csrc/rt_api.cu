@@ -191,8 +191,8 @@ struct rt_tree
   std::vector<cudaEvent_t> events; // EV_COUNT per batch of a call, grow-only
 
   Slot slot[NSLOT];
-  DevBuf d_ray_t, d_ray_id, d_ray_any;
-  HostBuf h_offsets, h_ids, h_ray_t, h_ray_id, h_ray_any, h_batch_counters;
+  DevBuf d_ray_t, d_ray_id, d_ray_any, d_knn_ids, d_knn_d2;
+  HostBuf h_offsets, h_ids, h_ray_t, h_ray_id, h_ray_any, h_batch_counters, h_knn_ids, h_knn_d2;
   uint64_t pipeline_batch = DEFAULT_PIPELINE_BATCH;
   uint32_t query_chunk = 0, work_ranges = 0; // 0 = the kernels' defaults
   int traverse_grid = 0;                     // 0 = fill the GPU
@@ -641,10 +641,11 @@ void rt_free(rt_tree* t)
       cudaStreamSynchronize(s.stream);
     s.release();
   }
-  DevBuf* dev[] = { &t->d_ray_t, &t->d_ray_id, &t->d_ray_any };
+  DevBuf* dev[] = { &t->d_ray_t, &t->d_ray_id, &t->d_ray_any, &t->d_knn_ids, &t->d_knn_d2 };
   for (DevBuf* b : dev)
     b->release();
-  HostBuf* host[] = { &t->h_offsets, &t->h_ids, &t->h_ray_t, &t->h_ray_id, &t->h_ray_any, &t->h_batch_counters };
+  HostBuf* host[] = { &t->h_offsets, &t->h_ids,  &t->h_ray_t,    &t->h_ray_id, &t->h_ray_any, &t->h_batch_counters,
+                      &t->h_knn_ids, &t->h_knn_d2 };
   for (HostBuf* b : host)
     b->release();
   if (t->d_blocks)
@@ -1204,6 +1205,143 @@ int rt_query_rays(rt_tree* t, const float* rays, uint64_t n, uint32_t mode, uint
     const uint64_t b_int = M * (2 * 3 * 4 + 4);
     const uint64_t b_leaf = t->desc.key_kind == RT_KEY_BOX ? b_int : M * (3 * 4 + 4);
     s.algorithmic_bytes = hc.visits[0] * b_int + hc.visits[1] * b_leaf + n * (28 + 8) + 4 * total;
+  }
+  return RT_OK;
+}
+
+int rt_query_knn(rt_tree* t, const float* points, uint64_t n, uint32_t k, uint32_t flags, rt_knn_result* out)
+{
+  if (t == nullptr || out == nullptr)
+    return fail(RT_E_INVALID, "rt_query_knn: NULL argument");
+  if (points == nullptr && n > 0)
+    return fail(RT_E_INVALID, "rt_query_knn: points is NULL");
+  if (k < 1 || k > 32)
+    return fail(RT_E_INVALID, "rt_query_knn: k must be 1..32");
+  if (!rtb::knn_supported(t->desc.scalar, t->desc.dim, t->desc.width))
+    return fail(RT_E_UNSUPPORTED, "rt_query_knn: kNN queries need a float32 tree with dim 2 or 3 and 8-wide blocks");
+  if (n >= 0xFFFFFFFFull)
+    return fail(RT_E_INVALID, "rt_query_knn: at most 2^32-2 queries per call");
+  int rc = use_device(t);
+  if (rc != RT_OK)
+    return rc;
+
+  std::memset(out, 0, sizeof *out);
+  std::memset(&t->stats, 0, sizeof t->stats);
+  cudaStream_t st = t->stream;
+  Slot& w = t->slot[0];
+  cudaEvent_t* ev = nullptr;
+  if ((rc = batch_events(t, 0, &ev)) != RT_OK)
+    return rc;
+  const uint32_t dim = t->desc.dim;
+  const size_t point_bytes = (size_t)n * dim * sizeof(float);
+  const size_t out_elems = (size_t)n * k;
+  const bool on_device = (flags & RT_QUERIES_ON_DEVICE) != 0;
+  const bool keep_on_device = (flags & RT_RESULT_ON_DEVICE) != 0;
+  const bool collect = (flags & RT_COLLECT_VISITS) != 0;
+  const bool reorder = (flags & RT_NO_REORDER) == 0 && n >= 4096;
+  uint32_t launches = 0;
+
+  RT_CUDA(w.d_counters.reserve(sizeof(Counters)));
+  RT_CUDA(w.d_cursors.reserve(rtb::MAX_WORK_RANGES * sizeof(unsigned int)));
+  RT_CUDA(w.h_counters.reserve(sizeof(Counters)));
+  if (!on_device)
+    RT_CUDA(w.d_queries.reserve(point_bytes ? point_bytes : 16));
+  if (reorder)
+  {
+    RT_CUDA(w.d_order.reserve((size_t)n * sizeof(uint32_t)));
+    RT_CUDA(w.d_scratch.reserve(rtb::reorder_scratch_bytes(n)));
+  }
+  RT_CUDA(t->d_knn_ids.reserve((out_elems + 1) * sizeof(uint32_t)));
+  RT_CUDA(t->d_knn_d2.reserve((out_elems + 1) * sizeof(float)));
+
+  RT_CUDA(cudaEventRecord(ev[EV_BEGIN], st));
+  const float* d_points = points;
+  if (!on_device)
+  {
+    if (point_bytes)
+      RT_CUDA(cudaMemcpyAsync(w.d_queries.p, points, point_bytes, cudaMemcpyHostToDevice, st));
+    d_points = w.d_queries.as<float>();
+  }
+  RT_CUDA(cudaMemsetAsync(w.d_counters.p, 0, sizeof(Counters), st));
+  RT_CUDA(cudaEventRecord(ev[EV_H2D], st));
+  const uint32_t* d_order = nullptr;
+  if (reorder)
+  {
+    // the coherence pass of the box queries, with the point as its own centre
+    RT_CUDA(rtb::launch_reorder(d_points, RT_F32, dim, dim, n, w.d_order.as<uint32_t>(), w.d_scratch.p, st,
+                                &launches, 0u));
+    d_order = w.d_order.as<uint32_t>();
+  }
+  RT_CUDA(cudaEventRecord(ev[EV_REORDER], st));
+
+  Counters* dc = w.d_counters.as<Counters>();
+  rtb::KnnLaunch L;
+  std::memset(&L, 0, sizeof L);
+  L.tree = t->dev;
+  L.points = d_points;
+  L.order = d_order;
+  L.n = n;
+  L.k = k;
+  L.collect = collect ? 1u : 0u;
+  L.ids_out = t->d_knn_ids.as<uint32_t>();
+  L.d2_out = t->d_knn_d2.as<float>();
+  L.work.cursors = w.d_cursors.as<unsigned int>();
+  L.work.chunk = t->query_chunk;
+  L.work.ranges = t->work_ranges;
+  L.visit_stats = dc->visits;
+  L.grid = t->traverse_grid;
+  L.stream = st;
+  if (n > 0)
+  {
+    RT_CUDA(rtb::launch_knn_kernel(L, dim, t->desc.width, t->desc.key_kind));
+    ++launches;
+  }
+  RT_CUDA(cudaEventRecord(ev[EV_TRAVERSE], st));
+  RT_CUDA(cudaMemcpyAsync(w.h_counters.p, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaEventRecord(ev[EV_FINISH], st));
+
+  out->n_queries = n;
+  out->k = k;
+  if (keep_on_device)
+  {
+    out->ids = t->d_knn_ids.as<uint32_t>();
+    out->dist2 = t->d_knn_d2.as<float>();
+    out->memory = RT_MEM_DEVICE;
+  }
+  else
+  {
+    RT_CUDA(t->h_knn_ids.reserve((out_elems + 1) * sizeof(uint32_t)));
+    RT_CUDA(t->h_knn_d2.reserve((out_elems + 1) * sizeof(float)));
+    if (out_elems)
+    {
+      RT_CUDA(cudaMemcpyAsync(t->h_knn_ids.p, t->d_knn_ids.p, out_elems * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      RT_CUDA(cudaMemcpyAsync(t->h_knn_d2.p, t->d_knn_d2.p, out_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    out->ids = t->h_knn_ids.as<uint32_t>();
+    out->dist2 = t->h_knn_d2.as<float>();
+    out->memory = RT_MEM_HOST;
+  }
+  RT_CUDA(cudaEventRecord(ev[EV_D2H], st));
+  RT_CUDA(cudaStreamSynchronize(st));
+
+  const Counters hc = *w.h_counters.as<Counters>();
+  rt_stats& s = t->stats;
+  s.total_ms = elapsed(ev[EV_BEGIN], ev[EV_D2H]);
+  s.batches = 1;
+  s.h2d_ms = elapsed(ev[EV_BEGIN], ev[EV_H2D]);
+  s.reorder_ms = elapsed(ev[EV_H2D], ev[EV_REORDER]);
+  s.traverse_ms = elapsed(ev[EV_REORDER], ev[EV_TRAVERSE]);
+  s.finish_ms = elapsed(ev[EV_TRAVERSE], ev[EV_FINISH]);
+  s.d2h_ms = elapsed(ev[EV_FINISH], ev[EV_D2H]);
+  s.kernel_launches = launches;
+  if (collect)
+  {
+    s.visits_internal = hc.visits[0];
+    s.visits_leaf = hc.visits[1];
+    const uint64_t M = t->desc.max_entries, D = dim;
+    const uint64_t b_int = M * (2 * D * 4 + 4);
+    const uint64_t b_leaf = t->desc.key_kind == RT_KEY_BOX ? b_int : M * (D * 4 + 4);
+    s.algorithmic_bytes = hc.visits[0] * b_int + hc.visits[1] * b_leaf + n * (D * 4 + 8ull * k);
   }
   return RT_OK;
 }

@@ -135,6 +135,24 @@ struct RayLaunch
 };
 cudaError_t launch_ray_kernel(const RayLaunch&); // rt_ray.cu; cudaErrorInvalidValue if unsupported
 
+struct KnnLaunch
+{
+  TreeDev tree;
+  const float* points;   // [n][dim]
+  const uint32_t* order; // nullable: i-th processed query is order[i]
+  uint64_t n;
+  uint32_t k;            // 1 .. 32
+  uint32_t collect;      // also count node visits
+  uint32_t* ids_out;     // [n][k]
+  float* d2_out;         // [n][k]
+  WorkRanges work;
+  unsigned long long* visit_stats;
+  int grid;
+  cudaStream_t stream;
+};
+bool knn_supported(uint32_t scalar, uint32_t dim, uint32_t width); // rt_knn.cu
+cudaError_t launch_knn_kernel(const KnnLaunch&, uint32_t dim, uint32_t width, uint32_t key_kind);
+
 // grid of a persistent traversal launch (occupancy x SMs, clamped to the work) and the split of
 // the n queries into ranges; zeroes the cursors on `stream`.  On entry work.chunk / work.ranges
 // hold the caller's wishes (0 = default: QUERY_CHUNK, one range per SM).
@@ -167,8 +185,10 @@ cudaError_t launch_sort_segments(const uint32_t* big_list, const uint32_t* big_c
 // coherence pass: order[] = query indices grouped by the Morton cell of the box centre
 // (first 3 axes), cells sized from the batch's own extent; scratch >= reorder_scratch_bytes()
 size_t reorder_scratch_bytes(uint64_t n);
+// hi_offset: where the second corner of a query starts (dim for boxes; 0 for points, whose centre is
+// the point itself)
 cudaError_t launch_reorder(const void* queries, uint32_t scalar, uint32_t dim, uint32_t floats_per_query,
                            uint64_t n, uint32_t* order, void* scratch, cudaStream_t stream,
-                           uint32_t* launches);
+                           uint32_t* launches, uint32_t hi_offset = 0xFFFFFFFFu);
 
 } // namespace rtb

@@ -348,10 +348,11 @@ namespace
 constexpr uint32_t CELL_BITS_PER_AXIS = 7;                       // 128 cells per axis
 constexpr uint32_t CELL_COUNT = 1u << (3 * CELL_BITS_PER_AXIS);  // 2 M cells
 
+// `hi` = offset of the second corner in the query record (0 for a point: the centre is the point)
 template <typename S>
-__device__ __forceinline__ float centre_of(const S* q, uint32_t dim, uint32_t axis)
+__device__ __forceinline__ float centre_of(const S* q, uint32_t hi, uint32_t axis)
 {
-  return 0.5f * ((float)q[axis] + (float)q[dim + axis]);
+  return 0.5f * ((float)q[axis] + (float)q[hi + axis]);
 }
 
 __device__ __forceinline__ uint32_t spread3(uint32_t v)
@@ -394,8 +395,8 @@ __global__ void reorder_init(ReorderScratch* s, uint32_t* cell_count)
 }
 
 template <typename S>
-__global__ void __launch_bounds__(256) reorder_extent(const S* __restrict__ q, uint32_t dim, uint32_t stride,
-                                                      uint64_t n, ReorderScratch* s)
+__global__ void __launch_bounds__(256) reorder_extent(const S* __restrict__ q, uint32_t dim, uint32_t hi_at,
+                                                      uint32_t stride, uint64_t n, ReorderScratch* s)
 {
   const uint32_t axes = dim < 3 ? dim : 3;
   float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(256) reorder_extent(const S* __restrict__ q, u
   {
     for (uint32_t a = 0; a < axes; ++a)
     {
-      const float c = centre_of(q + i * stride, dim, a);
+      const float c = centre_of(q + i * stride, hi_at, a);
       if (c == c && fabsf(c) != INFINITY)
       {
         lo[a] = fminf(lo[a], c);
@@ -427,15 +428,15 @@ __global__ void __launch_bounds__(256) reorder_extent(const S* __restrict__ q, u
 }
 
 template <typename S>
-__device__ __forceinline__ uint32_t cell_of(const S* q, uint32_t dim, const ReorderScratch* s)
+__device__ __forceinline__ uint32_t cell_of(const S* q, uint32_t dim, uint32_t hi, const ReorderScratch* s)
 {
   const uint32_t axes = dim < 3 ? dim : 3;
   uint32_t code = 0;
   for (uint32_t a = 0; a < axes; ++a)
   {
-    const float lo = key_float(s->ext_min[a]), hi = key_float(s->ext_max[a]);
-    const float c = centre_of(q, dim, a);
-    float t = (hi > lo) ? (c - lo) / (hi - lo) : 0.0f;
+    const float lo = key_float(s->ext_min[a]), vhi = key_float(s->ext_max[a]);
+    const float c = centre_of(q, hi, a);
+    float t = (vhi > lo) ? (c - lo) / (vhi - lo) : 0.0f;
     t = (t == t) ? fminf(fmaxf(t, 0.0f), 1.0f) : 0.0f;
     const uint32_t cell = min((uint32_t)(t * (float)(1u << CELL_BITS_PER_AXIS)), (1u << CELL_BITS_PER_AXIS) - 1u);
     code |= spread3(cell) << a;
@@ -444,13 +445,13 @@ __device__ __forceinline__ uint32_t cell_of(const S* q, uint32_t dim, const Reor
 }
 
 template <typename S>
-__global__ void __launch_bounds__(256) reorder_histogram(const S* __restrict__ q, uint32_t dim, uint32_t stride,
-                                                         uint64_t n, const ReorderScratch* s,
+__global__ void __launch_bounds__(256) reorder_histogram(const S* __restrict__ q, uint32_t dim, uint32_t hi,
+                                                         uint32_t stride, uint64_t n, const ReorderScratch* s,
                                                          uint32_t* cell_count, uint32_t* cell_of_query)
 {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
   {
-    const uint32_t c = cell_of(q + i * stride, dim, s);
+    const uint32_t c = cell_of(q + i * stride, dim, hi, s);
     cell_of_query[i] = c;
     atomicAdd(&cell_count[c], 1u);
   }
@@ -488,10 +489,11 @@ size_t reorder_scratch_bytes(uint64_t n)
 
 cudaError_t launch_reorder(const void* queries, uint32_t scalar, uint32_t dim, uint32_t scalars_per_query,
                            uint64_t n, uint32_t* order, void* scratch, cudaStream_t stream,
-                           uint32_t* launches)
+                           uint32_t* launches, uint32_t hi_offset)
 {
   if (n == 0)
     return cudaSuccess;
+  const uint32_t hi = hi_offset == 0xFFFFFFFFu ? dim : hi_offset;
   unsigned char* base = static_cast<unsigned char*>(scratch);
   ReorderScratch* rs = reinterpret_cast<ReorderScratch*>(base);
   base += align256(sizeof(ReorderScratch));
@@ -509,18 +511,18 @@ cudaError_t launch_reorder(const void* queries, uint32_t scalar, uint32_t dim, u
   switch (scalar)
   {
   case RT_F32:
-    reorder_extent<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(queries), dim, scalars_per_query, n, rs);
-    reorder_histogram<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(queries), dim, scalars_per_query, n,
+    reorder_extent<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(queries), dim, hi, scalars_per_query, n, rs);
+    reorder_histogram<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(queries), dim, hi, scalars_per_query, n,
                                                        rs, cell_count, cell_of_query);
     break;
   case RT_F64:
-    reorder_extent<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(queries), dim, scalars_per_query, n, rs);
-    reorder_histogram<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(queries), dim, scalars_per_query,
+    reorder_extent<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(queries), dim, hi, scalars_per_query, n, rs);
+    reorder_histogram<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(queries), dim, hi, scalars_per_query,
                                                         n, rs, cell_count, cell_of_query);
     break;
   case RT_I32:
-    reorder_extent<int32_t><<<grid, 256, 0, stream>>>(static_cast<const int32_t*>(queries), dim, scalars_per_query, n, rs);
-    reorder_histogram<int32_t><<<grid, 256, 0, stream>>>(static_cast<const int32_t*>(queries), dim, scalars_per_query,
+    reorder_extent<int32_t><<<grid, 256, 0, stream>>>(static_cast<const int32_t*>(queries), dim, hi, scalars_per_query, n, rs);
+    reorder_histogram<int32_t><<<grid, 256, 0, stream>>>(static_cast<const int32_t*>(queries), dim, hi, scalars_per_query,
                                                          n, rs, cell_count, cell_of_query);
     break;
   default: return cudaErrorInvalidValue;

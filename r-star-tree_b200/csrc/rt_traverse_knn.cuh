@@ -1,0 +1,212 @@
+// rt_traverse_knn.cuh -- warp-cooperative k-nearest-neighbour queries on the float blocks (sm_100a).
+//
+// The reference has no kNN code; the query is RTree::search() (reference
+// include/RTree/rtree.hpp:984-1019) driven by stateful functors (legal: they are held by
+// reference, rtree.hpp:1145), defined operation for operation in oracle/knn.h:
+//   filter  : descend iff dist2(q, child bound) <= worst.d2 (non-strict: ties survive, so the
+//             answer does not depend on the traversal order)
+//   functor : a key with (d2, id) < worst replaces the worst of the k best pairs
+//   result  : the k pairs ascending by (d2, id), missing ones (+inf, RT_INVALID_ID)
+//   dist2   : per axis e = (q < lo) ? lo - q : ((q > hi) ? q - hi : 0); d2 = d2 + e * e
+//             (float32, round to nearest, axis 0 first, never fused)
+//
+// Mapping and stack discipline are those of rt_traverse_box.cuh (one warp per query, G = 32/W
+// nodes per step, one lane per child slot, null node below the stack).  Differences:
+//   * a stack entry is (link, dist2 of the node's bound): entries that the shrinking bound has
+//     overtaken since they were pushed are dropped when popped;
+//   * the children of one node are pushed far-ones-first, so the nearest are popped next and the
+//     bound tightens early (children of different nodes keep their order: the stack stays sorted
+//     by level, which is what bounds its depth);
+//   * the k best pairs live one per lane (k <= 32); the worst is found with two warp reductions
+//     and the candidates of a leaf step are offered one at a time.
+#pragma once
+
+#include "rt_block.cuh"
+#include "rt_common.cuh"
+
+namespace rtb
+{
+
+__device__ __forceinline__ void lds_u32x2(uint32_t addr, uint32_t& a, uint32_t& b)
+{
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts_u32x2(uint32_t addr, uint32_t a, uint32_t b)
+{
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+// ascending bitonic sort of one (hi, lo) 64-bit key per lane
+__device__ __forceinline__ void warp_sort32_pair(uint32_t& hi, uint32_t& lo, int lane)
+{
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1)
+  {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1)
+    {
+      const uint32_t ohi = __shfl_xor_sync(0xFFFFFFFFu, hi, j);
+      const uint32_t olo = __shfl_xor_sync(0xFFFFFFFFu, lo, j);
+      const bool ascending = (lane & k) == 0;
+      const bool lower = (lane & j) == 0;
+      const bool mine_less = hi < ohi || (hi == ohi && lo < olo);
+      const bool other_less = ohi < hi || (ohi == hi && olo < lo);
+      if ((lower == ascending) ? other_less : mine_less) // keep the smaller / the larger of the two
+      {
+        hi = ohi;
+        lo = olo;
+      }
+    }
+  }
+}
+
+template <int D, int W, bool BOXKEY>
+__global__ void __launch_bounds__(TRAVERSE_THREADS)
+knn_traverse_kernel(const KnnLaunch p)
+{
+  constexpr int G = 32 / W;
+  constexpr uint32_t INF_BITS = 0x7F800000u;
+  extern __shared__ uint32_t smem[];
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int slot = lane % W;
+  const uint32_t grp = lane / W;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t grp_mask = ((1u << W) - 1u) << (grp * W);
+
+  // per warp: G null entries, then the stack of (link, dist2 bits) pairs
+  const uint32_t stack_cap = 32u * p.tree.num_levels;
+  const uint32_t warp_mem = smem_addr(smem + warp * 2 * (G + stack_cap));
+  const uint32_t stack = warp_mem + G * 8u;
+  const uint32_t stack_pop = stack + (grp - G) * 8u;
+  const uint32_t null_link = p.tree.null_link;
+  if (lane < G)
+    sts_u32x2(warp_mem + lane * 8u, null_link, 0u);
+  __syncwarp();
+
+  const unsigned char* lane_blocks = opaque(p.tree.blocks + slot * 16);
+  const uint32_t leaf_link_begin = p.tree.leaf_link_begin;
+  const uint32_t k = p.k;
+  const bool holder = (uint32_t)lane < k; // this lane holds one of the k best pairs
+
+  unsigned long long visits_int = 0, visits_leaf = 0;
+
+  uint32_t range = (p.work.by_sm ? sm_id() : blockIdx.x) % p.work.ranges, tries = 0;
+  for (;;)
+  {
+    const uint32_t c = claim_chunk(p.work, range, lane);
+    const unsigned long long begin = (unsigned long long)range * p.work.per_range + c;
+    if (c >= p.work.per_range || begin >= p.n)
+    {
+      if (++tries >= p.work.ranges)
+        break;
+      range = range + 1 == p.work.ranges ? 0 : range + 1;
+      continue;
+    }
+    const unsigned long long last = min(begin + p.work.chunk, (unsigned long long)p.n);
+
+    for (unsigned long long i = begin; i < last; ++i)
+    {
+      const unsigned long long qi = p.order ? (unsigned long long)p.order[i] : i;
+      float q[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+        q[d] = __ldg(p.points + qi * D + d);
+
+      uint32_t bd2 = INF_BITS, bid = RT_INVALID_ID;       // this lane's pair (holders only)
+      uint32_t wd = INF_BITS, wi = RT_INVALID_ID, wl = 0; // the worst pair and the lane that holds it
+
+      uint32_t sp8 = 8u; // bytes on the stack
+      if (lane == 0)
+        sts_u32x2(stack, 0u, 0u); // the root; its own bound is never tested (reference rtree.hpp:984)
+      __syncwarp();
+
+      while (sp8 != 0)
+      {
+        uint32_t node, node_d2;
+        lds_u32x2(stack_pop + sp8, node, node_d2);
+        sp8 -= min(sp8, (uint32_t)(G * 8));
+        __syncwarp();
+        if (node_d2 > wd) // the bound has moved past this node since it was pushed (d2 >= +0: bits order)
+          node = null_link;
+
+        const bool is_leaf = node >= leaf_link_begin;
+        uint32_t link;
+        float lo[D], hi[D];
+        load_entry<float, D, W, BOXKEY>(lane_blocks + (unsigned long long)node * 16u, slot, is_leaf, lo, hi, link);
+        float d2 = 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+        {
+          const float e = (q[d] < lo[d]) ? __fsub_rn(lo[d], q[d]) : ((q[d] > hi[d]) ? __fsub_rn(q[d], hi[d]) : 0.0f);
+          d2 = __fadd_rn(d2, __fmul_rn(e, e));
+        }
+        const uint32_t d2b = __float_as_uint(d2);
+        const bool valid = link != RT_INVALID_ID;
+
+        if (p.collect)
+        {
+          visits_leaf += __popc(__ballot_sync(0xFFFFFFFFu, is_leaf && slot == 0 && node != null_link));
+          visits_int += __popc(__ballot_sync(0xFFFFFFFFu, !is_leaf && slot == 0));
+        }
+
+        // ---- children to descend: those the bound has not excluded, far ones of a node first ------
+        const bool push = valid && !is_leaf && d2b <= wd;
+        const uint32_t m_push = __ballot_sync(0xFFFFFFFFu, push);
+        if (m_push != 0)
+        {
+          const uint32_t dmin = __reduce_min_sync(grp_mask, push ? d2b : 0xFFFFFFFFu);
+          const bool is_far = push && d2 > __fmul_rn(__uint_as_float(dmin), 4.0f);
+          const uint32_t m_far = __ballot_sync(0xFFFFFFFFu, is_far);
+          const uint32_t below = __popc(m_push & ~grp_mask & lt_mask); // pushes of the lower groups
+          const uint32_t far_g = m_far & grp_mask, near_g = m_push & ~m_far & grp_mask;
+          const uint32_t at = below + (is_far ? __popc(far_g & lt_mask) : __popc(far_g) + __popc(near_g & lt_mask));
+          if (push)
+            sts_u32x2(stack + sp8 + at * 8u, link, d2b);
+          sp8 += __popc(m_push) * 8u;
+        }
+
+        // ---- leaf entries that beat the worst of the k best: offered one at a time -----------------
+        uint32_t m_cand = __ballot_sync(0xFFFFFFFFu, valid && is_leaf && (d2b < wd || (d2b == wd && link < wi)));
+        while (m_cand != 0)
+        {
+          const int src = __ffs(m_cand) - 1;
+          m_cand &= m_cand - 1;
+          const uint32_t cd = __shfl_sync(0xFFFFFFFFu, d2b, src);
+          const uint32_t ci = __shfl_sync(0xFFFFFFFFu, link, src);
+          if (cd < wd || (cd == wd && ci < wi))
+          {
+            if ((uint32_t)lane == wl)
+            {
+              bd2 = cd;
+              bid = ci;
+            }
+            wd = __reduce_max_sync(0xFFFFFFFFu, holder ? bd2 : 0u);
+            wi = __reduce_max_sync(0xFFFFFFFFu, (holder && bd2 == wd) ? bid : 0u);
+            wl = (uint32_t)__ffs(__ballot_sync(0xFFFFFFFFu, holder && bd2 == wd && bid == wi)) - 1u;
+          }
+        }
+        __syncwarp();
+      }
+
+      // ---- the k pairs, ascending by (d2, id) ---------------------------------------------------
+      uint32_t sd = holder ? bd2 : 0xFFFFFFFFu, si = holder ? bid : 0xFFFFFFFFu;
+      warp_sort32_pair(sd, si, lane);
+      if (holder)
+      {
+        p.ids_out[qi * k + lane] = si;
+        p.d2_out[qi * k + lane] = __uint_as_float(sd);
+      }
+      __syncwarp();
+    }
+  }
+
+  if (p.collect && lane == 0)
+  {
+    atomicAdd(p.visit_stats + 0, visits_int);
+    atomicAdd(p.visit_stats + 1, visits_leaf);
+  }
+}
+
+} // namespace rtb

@@ -94,5 +94,32 @@ def main():
     boxes_case("lattice_2d_i32", 8, g, np.stack([lo, hi], axis=1), O.MODE_POINT_IN_BOX)
 
 
+def knn_cases():
+    """kNN (oracle/knn.h) through the reference's search(): 3-D points with duplicate keys (ties), 2-D
+    points, 3-D box keys; k = 1, 8, 32; query points include exact data points."""
+    rng = np.random.default_rng(17)
+    pts3 = W.uniform_points(20000, seed=48)
+    pts3[:300] = pts3[300:600]
+    pts2 = rng.random((8000, 2)).astype(np.float32)
+    boxes = W.triangle_aabbs(W.teapot_triangles(0.5))
+    for name, kind, keys, lo, hi in (("knn_points_3d", 4, pts3, 0.0, 1.0), ("knn_points_2d", 3, pts2, -0.2, 1.2),
+                                     ("knn_boxes_3d", 5, boxes, -3.5, 3.5)):
+        t = O.RefTree(kind).insert(keys)
+        dim = keys.shape[-1]
+        q = rng.uniform(lo, hi, (1500, dim)).astype(np.float32)
+        if kind != 5:
+            q[:200] = keys[:200]
+        extra = {}
+        for k in (1, 8, 32):
+            ids, d2 = t.search_knn(q, k)
+            extra["ids_k%d" % k] = ids
+            extra["d2_k%d" % k] = d2
+        save(name, t.flatten(), kind=kind, keys=keys, points=q, **extra)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "knn":
+        knn_cases()
+    else:
+        main()
+        knn_cases()

@@ -79,6 +79,9 @@ def ref_lib():
         lib.ref_search_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int,
                                         C.c_void_p, _u32pp, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_double)]
+        lib.ref_search_knn.restype = C.c_int64
+        lib.ref_search_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         lib.ref_free.argtypes = [C.c_void_p]
         lib.ref_max_threads.restype = C.c_int
         _ref_lib = lib
@@ -110,6 +113,12 @@ def oracle_lib():
         lib.oracle_brute_rays.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                           C.c_int, C.c_void_p, _u32pp, C.c_void_p, C.c_void_p,
                                           C.c_void_p]
+        lib.oracle_query_knn.restype = C.c_int64
+        lib.oracle_query_knn.argtypes = [C.POINTER(OracleFlat), C.c_int, C.c_void_p, C.c_uint64, C.c_uint32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_brute_knn.restype = C.c_int64
+        lib.oracle_brute_knn.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p,
+                                         C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.oracle_free.argtypes = [C.c_void_p]
         _oracle_lib = lib
     return _oracle_lib
@@ -246,8 +255,46 @@ class RefTree:
         return (sec.value, int(total)) if timed_only else anyhit
 
 
+    def search_knn(self, points, k, threads=0, timed_only=False):
+        """kNN through the reference's search() (oracle/knn.h) -> (ids[n][k], d2[n][k])."""
+        p = np.ascontiguousarray(points, np.float32).reshape(-1, self.dim)
+        ids = np.zeros((len(p), k), np.uint32)
+        d2 = np.zeros((len(p), k), np.float32)
+        sec = C.c_double(0)
+        rc = self.lib.ref_search_knn(self.h, _ptr(p), len(p), k, threads, _ptr(ids), _ptr(d2), C.byref(sec))
+        assert rc == 0, "kNN needs a float32 tree"
+        return sec.value if timed_only else (ids, d2)
+
+
 def ref_max_threads():
     return ref_lib().ref_max_threads()
+
+
+def oracle_query_knn(flat, points, k, want_visits=False):
+    lib = oracle_lib()
+    p = np.ascontiguousarray(points, np.float32).reshape(-1, flat.dim)
+    ids = np.zeros((len(p), k), np.uint32)
+    d2 = np.zeros((len(p), k), np.float32)
+    visits = np.zeros(2, np.uint64)
+    cs = flat.c_struct()
+    rc = lib.oracle_query_knn(C.byref(cs), int(flat.key_is_box), _ptr(p), len(p), k, _ptr(ids), _ptr(d2),
+                              _ptr(visits))
+    assert rc == 0
+    return (ids, d2, visits) if want_visits else (ids, d2)
+
+
+def oracle_brute_knn(keys, key_is_box, key_ids, dim, points, k):
+    lib = oracle_lib()
+    keys = np.ascontiguousarray(keys, np.float32)
+    n_keys = keys.size // (dim * (2 if key_is_box else 1))
+    key_ids = None if key_ids is None else np.ascontiguousarray(key_ids, np.uint32)
+    p = np.ascontiguousarray(points, np.float32).reshape(-1, dim)
+    ids = np.zeros((len(p), k), np.uint32)
+    d2 = np.zeros((len(p), k), np.float32)
+    rc = lib.oracle_brute_knn(_ptr(keys), n_keys, int(key_is_box), _ptr(key_ids), dim, _ptr(p), len(p), k,
+                              _ptr(ids), _ptr(d2))
+    assert rc == 0
+    return ids, d2
 
 
 def oracle_query_boxes(flat, queries, mode=MODE_POINT_IN_BOX, want_visits=False):

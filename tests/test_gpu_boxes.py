@@ -319,8 +319,8 @@ def test_quantised_image_gives_the_exact_hit_sets(rtb, case):
         pts[1] = [-3e38, 3e38, -3e38]
     elif case == "duplicates":
         pts = pts[rng.integers(0, 50, n)]                  # 50 distinct points, long equal runs
-    span = pts.max(axis=0) - pts.min(axis=0)
     with np.errstate(over="ignore", invalid="ignore"):
+        span = pts.max(axis=0) - pts.min(axis=0)
         c = pts[rng.integers(0, len(pts), 3000)]
         h = (np.where(np.isfinite(span), span, np.float32(1e30)) * np.float32(0.02)).astype(np.float32)
         q = np.concatenate([

@@ -33,9 +33,12 @@ BOX_FIXTURES = ["flatten_test_1d_i32", "sample_1d_f64", "config1_2d_f64", "confi
                 "config4_cut_8d_f32", "teapot_boxes_intersects", "teapot_boxes_contains", "lattice_2d_i32"]
 
 
+KNN_FIXTURES = ["knn_points_3d", "knn_points_2d", "knn_boxes_3d"]
+
+
 def test_all_fixtures_present():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    assert names == sorted(BOX_FIXTURES + ["teapot_rays"])
+    assert names == sorted(BOX_FIXTURES + ["teapot_rays"] + KNN_FIXTURES)
 
 
 @pytest.mark.parametrize("name", BOX_FIXTURES)
@@ -247,3 +250,36 @@ def test_visit_counters_define_algorithmic_bytes():
     v_int, v_leaf, tests = [int(x) for x in visits]
     assert v_int >= 500 * flat.leaf_level and v_leaf > 0 and tests >= v_int + v_leaf
     assert ids.size > 0
+
+
+@pytest.mark.parametrize("name", KNN_FIXTURES)
+def test_knn_restatement_and_brute_force_match_golden(name):
+    """kNN has no reference code: the golden vectors come from the reference's search() driven by the
+    functors of oracle/knn.h; the flat-form restatement and the O(N*Q) brute force must agree with
+    them bit for bit (ids and float32 distances), ties by the smaller id"""
+    z, flat = load(name)
+    q = z["points"]
+    for k in (1, 8, 32):
+        ids, d2 = O.oracle_query_knn(flat, q, k)
+        assert np.array_equal(ids, z["ids_k%d" % k])
+        assert np.array_equal(d2.view(np.uint32), z["d2_k%d" % k].view(np.uint32))
+        sub = slice(0, 300)
+        bi, bd = O.oracle_brute_knn(z["keys"], flat.key_is_box, None, flat.dim, q[sub], k)
+        assert np.array_equal(bi, z["ids_k%d" % k][sub])
+        assert np.array_equal(bd.view(np.uint32), z["d2_k%d" % k][sub].view(np.uint32))
+    assert np.all(np.diff(z["d2_k32"], axis=1) >= 0)
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="reference oracle not built")
+def test_knn_through_reference_search_live():
+    rng = np.random.default_rng(33)
+    pts = rng.random((7000, 3)).astype(np.float32)
+    q = rng.random((400, 3)).astype(np.float32)
+    ref = O.RefTree(4).insert(pts)
+    flat = ref.flatten()
+    for k in (3, 17):
+        a, b = ref.search_knn(q, k), O.oracle_query_knn(flat, q, k)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    few = O.RefTree(4).insert(pts[:5])
+    ids, d2 = few.search_knn(q[:10], 8)
+    assert np.all(ids[:, 5:] == 0xFFFFFFFF) and np.all(np.isinf(d2[:, 5:])) and np.all(ids[:, :5] < 5)
