@@ -447,7 +447,7 @@ def main():
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": dram_traffic_per_launch(),
-                         "kernel": "rtb::box_traverse_kernel<float,3,8,false,false,PASS_STASH>",
+                         "kernel": "rtb::box_traverse_kernel<float,3,8,false,false,PASS_STASH,QUANT>",
                          "kernel_ms": trav_ms, "algorithmic_bytes_per_launch": alg_all / world,
                          "algorithmic_bytes_per_query": alg_all / world / nq,
                          "visits_per_query": {"internal": visit_stats["visits_internal"] / nq,
