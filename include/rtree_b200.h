@@ -224,6 +224,16 @@ typedef struct rt_knn_result
 int rt_query_knn(rt_tree* tree, const float* points, uint64_t n, uint32_t k, uint32_t flags,
                  rt_knn_result* out);
 
+/* Moving objects: replace every key and refit every bound on the device, keeping
+ * the topology -- the batch form of changing keys through the iterators and calling
+ * RTree::rebound(iterator) for each (reference README.md:342-347, include/RTree/rtree.hpp:479-500).
+ * keys: [n_keys] keys of the tree's kind ([dim] scalars for points, [2][dim] for boxes) in
+ * flatten_result_t::data order, i.e. the iteration order of RTree::begin()..end(); n_keys must be
+ * the tree's num_values.  Afterwards the device image equals flatten_device() of the refitted host
+ * tree byte for byte.  Like rebound() it does not rebalance: query cost degrades as keys drift.
+ * Flags: RT_QUERIES_ON_DEVICE (keys is device memory).                                       */
+int rt_refit(rt_tree* tree, const void* keys, uint64_t n_keys, uint32_t flags);
+
 /* Release the handle and every buffer it handed out.  NULL is a no-op.                */
 void rt_free(rt_tree* tree);
 

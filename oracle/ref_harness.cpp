@@ -75,6 +75,7 @@ struct ITree
 {
   virtual ~ITree() {}
   virtual void insert(const void* keys, uint64_t n, uint32_t first_id) = 0;
+  virtual int64_t set_keys(const void* keys, uint64_t n) = 0;
   virtual uint32_t leaf_level() const = 0;
   virtual uint64_t size() const = 0;
   virtual void rebalance() = 0;
@@ -153,6 +154,26 @@ struct TreeImpl : ITree
                           first_id + (uint32_t)i));
     }
     have_flat = false;
+  }
+  // "Dealing with moving objects" (reference README.md:342-347): keys are changed in place through
+  // the iterators (iteration order = flatten_result_t::data order) and RTree::rebound(iterator)
+  // (include/RTree/rtree.hpp:497-500) refits the ancestors; no topology change
+  int64_t set_keys(const void* keys, uint64_t n) override
+  {
+    const S* p = static_cast<const S*>(keys);
+    uint64_t i = 0;
+    for (auto it = tree.begin(); it != tree.end(); ++it, ++i)
+    {
+      if (i >= n)
+        return -1;
+      it->first = make_key(p + i * KEY_SCALARS, std::integral_constant<bool, KEY_IS_BOX> {});
+    }
+    if (i != n)
+      return -1;
+    for (auto it = tree.begin(); it != tree.end(); ++it)
+      tree.rebound(it);
+    have_flat = false;
+    return (int64_t)i;
   }
   uint32_t leaf_level() const override { return (uint32_t)tree.leaf_level(); }
   uint64_t size() const override { return tree.size(); }
@@ -600,6 +621,10 @@ extern "C"
     return static_cast<ITree*>(h)->search_rays(rays, n, mode, threads, offsets,
                                                ids, t_out, id_out, any_out,
                                                seconds);
+  }
+  int64_t ref_tree_set_keys(void* h, const void* keys, uint64_t n)
+  {
+    return static_cast<ITree*>(h)->set_keys(keys, n);
   }
   int64_t ref_search_knn(void* h, const float* points, uint64_t n, uint32_t k, int threads,
                          uint32_t* ids_out, float* d2_out, double* seconds)

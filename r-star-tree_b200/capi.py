@@ -29,7 +29,7 @@ RT_OPT_QUANTISED = 5
 SCALAR_DTYPES = {RT_F32: np.float32, RT_F64: np.float64, RT_I32: np.int32}
 
 # every symbol include/rtree_b200.h declares
-EXPORTS = ["rt_upload", "rt_query_boxes", "rt_query_rays", "rt_query_knn", "rt_free", "rt_set_stream",
+EXPORTS = ["rt_upload", "rt_query_boxes", "rt_query_rays", "rt_query_knn", "rt_refit", "rt_free", "rt_set_stream",
            "rt_set_option", "rt_get_stats", "rt_tree_device_blocks", "rt_tree_get_desc", "rt_last_error",
            "rt_abi_version", "rt_device_count"]
 
@@ -107,6 +107,8 @@ def lib():
         L.rt_query_knn.restype = C.c_int
         L.rt_query_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
                                    C.POINTER(RtKnnResult)]
+        L.rt_refit.restype = C.c_int
+        L.rt_refit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
         L.rt_set_stream.restype = C.c_int
         L.rt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.rt_set_option.restype = C.c_int
@@ -211,6 +213,12 @@ class DeviceTree:
         offsets = _host_array(out.offsets, out.n_queries + 1, np.uint64)
         ids = _host_array(out.ids, 0 if flags & RT_COUNT_ONLY else out.total, np.uint32)
         return offsets, ids
+
+    def refit(self, keys):
+        """rt_refit(): new keys (flatten data order) + all bounds recomputed on the device."""
+        per = self.dim * (2 if self.key_kind == RT_KEY_BOX else 1)
+        k = np.ascontiguousarray(keys, self.dtype).reshape(-1, per)
+        _check(lib().rt_refit(self._h, C.c_void_p(k.ctypes.data), len(k), 0))
 
     def query_knn_raw(self, points_ptr, n, k, flags=0):
         out = RtKnnResult()

@@ -57,6 +57,7 @@ struct TreeHandle
 {
   virtual ~TreeHandle() {}
   virtual void insert(const void* keys, uint64_t n, uint32_t first_id) = 0;
+  virtual int64_t set_keys(const void* keys, uint64_t n) = 0;
   virtual uint64_t erase_ids(const uint32_t* ids, uint64_t n) = 0;
   virtual void clear() = 0;
   virtual void rebalance() = 0;
@@ -123,6 +124,24 @@ struct Tree : TreeHandle
     for (uint64_t i = 0; i < n; ++i)
       tree.emplace(to_key(p + i * KEY_SCALARS, std::integral_constant<bool, BOXKEY> {}),
                    first_id + static_cast<uint32_t>(i));
+  }
+  // keys changed in place through the iterators (iteration order = flatten data order), then
+  // rebound() for every value: the host-side form of what rt_refit() does on the device
+  int64_t set_keys(const void* keys, uint64_t n) override
+  {
+    const S* p = static_cast<const S*>(keys);
+    uint64_t i = 0;
+    for (auto it = tree.begin(); it != tree.end(); ++it, ++i)
+    {
+      if (i >= n)
+        return -1;
+      it->first = to_key(p + i * KEY_SCALARS, std::integral_constant<bool, BOXKEY> {});
+    }
+    if (i != n)
+      return -1;
+    for (auto it = tree.begin(); it != tree.end(); ++it)
+      tree.rebound(it);
+    return (int64_t)i;
   }
   uint64_t erase_ids(const uint32_t* ids, uint64_t n) override
   {
@@ -347,6 +366,10 @@ extern "C"
   int rtb_tree_insert(void* h, const void* keys, uint64_t n, uint32_t first_id)
   {
     return guarded([&] { static_cast<TreeHandle*>(h)->insert(keys, n, first_id); return 0; }, -1);
+  }
+  int64_t rtb_tree_set_keys(void* h, const void* keys, uint64_t n)
+  {
+    return guarded([&] { return static_cast<TreeHandle*>(h)->set_keys(keys, n); }, (int64_t)-1);
   }
   int64_t rtb_tree_erase_ids(void* h, const uint32_t* ids, uint64_t n)
   {

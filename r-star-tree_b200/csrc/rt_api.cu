@@ -1346,6 +1346,57 @@ int rt_query_knn(rt_tree* t, const float* points, uint64_t n, uint32_t k, uint32
   return RT_OK;
 }
 
+int rt_refit(rt_tree* t, const void* keys, uint64_t n_keys, uint32_t flags)
+{
+  if (t == nullptr)
+    return fail(RT_E_INVALID, "rt_refit: tree is NULL");
+  if (n_keys != t->desc.num_values)
+    return fail(RT_E_INVALID, "rt_refit: n_keys must equal the tree's num_values");
+  if (keys == nullptr && n_keys > 0)
+    return fail(RT_E_INVALID, "rt_refit: keys is NULL");
+  int rc = use_device(t);
+  if (rc != RT_OK)
+    return rc;
+  std::memset(&t->stats, 0, sizeof t->stats);
+  cudaStream_t st = t->stream;
+  Slot& w = t->slot[0];
+  cudaEvent_t* ev = nullptr;
+  if ((rc = batch_events(t, 0, &ev)) != RT_OK)
+    return rc;
+  const bool on_device = (flags & RT_QUERIES_ON_DEVICE) != 0;
+  const size_t key_bytes = (size_t)n_keys * t->desc.dim * (t->desc.key_kind == RT_KEY_BOX ? 2 : 1)
+                           * (t->desc.scalar == RT_F64 ? 8u : 4u);
+  const uint32_t n_leaves = t->desc.num_nodes - t->levels[t->desc.leaf_level];
+  uint32_t launches = 0;
+  RT_CUDA(w.d_scratch.reserve(rtb::refit_scratch_bytes(n_leaves)));
+  if (!on_device)
+    RT_CUDA(w.d_queries.reserve(key_bytes ? key_bytes : 16));
+  RT_CUDA(cudaEventRecord(ev[EV_BEGIN], st));
+  const void* d_keys = keys;
+  if (!on_device)
+  {
+    if (key_bytes)
+      RT_CUDA(cudaMemcpyAsync(w.d_queries.p, keys, key_bytes, cudaMemcpyHostToDevice, st));
+    d_keys = w.d_queries.p;
+  }
+  RT_CUDA(cudaEventRecord(ev[EV_H2D], st));
+  RT_CUDA(rtb::launch_refit(t->d_blocks, t->desc, t->levels.data(), d_keys, w.d_scratch.p, st, &launches));
+  if (t->d_qblocks)
+  {
+    // the quantised image follows the float blocks (the grid is re-derived from the new root bounds)
+    RT_CUDA(rtb::build_quant_image(t->dev, t->levels[t->desc.leaf_level], t->desc.leaf_offset, t->d_qblocks, st));
+    launches += 2;
+  }
+  RT_CUDA(cudaEventRecord(ev[EV_TRAVERSE], st));
+  RT_CUDA(cudaStreamSynchronize(st));
+  t->stats.total_ms = elapsed(ev[EV_BEGIN], ev[EV_TRAVERSE]);
+  t->stats.h2d_ms = elapsed(ev[EV_BEGIN], ev[EV_H2D]);
+  t->stats.traverse_ms = elapsed(ev[EV_H2D], ev[EV_TRAVERSE]);
+  t->stats.kernel_launches = launches;
+  t->stats.batches = 1;
+  return RT_OK;
+}
+
 } // extern "C"
 
 namespace rtb

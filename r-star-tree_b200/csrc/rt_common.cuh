@@ -166,6 +166,11 @@ size_t quant_image_bytes(uint32_t num_nodes);
 cudaError_t build_quant_image(TreeDev& tree, uint32_t num_internal, uint64_t leaf_offset, unsigned char* qblocks,
                               cudaStream_t stream);
 
+// rt_refit.cu: new keys (flatten data order) into the leaf slots, then all bounds bottom-up
+size_t refit_scratch_bytes(uint32_t n_leaves);
+cudaError_t launch_refit(unsigned char* blocks, const rt_tree_desc& d, const uint32_t* levels, const void* keys,
+                         void* scratch, cudaStream_t stream, uint32_t* launches);
+
 // ---- rt_passes.cu -----------------------------------------------------------------
 // offsets[0..n] = exclusive prefix sum of counts[0..n) (64-bit); scratch >= scan_scratch_bytes(n)
 size_t scan_scratch_bytes(uint64_t n);

@@ -57,6 +57,8 @@ def lib():
         L.rtb_tree_erase_ids.restype = C.c_int64
         L.rtb_tree_erase_ids.argtypes = [vp, vp, u64]
         L.rtb_tree_clear.argtypes = [vp]
+        L.rtb_tree_set_keys.restype = C.c_int64
+        L.rtb_tree_set_keys.argtypes = [vp, vp, u64]
         L.rtb_tree_rebalance.argtypes = [vp]
         L.rtb_tree_leaf_level.restype = u32
         L.rtb_tree_leaf_level.argtypes = [vp]
@@ -178,6 +180,15 @@ class RTree:
         assert keys.size % per == 0
         if lib().rtb_tree_insert(self._h, _ptr(keys), keys.size // per, first_id) != 0:
             raise RuntimeError(_err())
+        return self
+
+    def set_keys(self, keys):
+        """change every key in place (iteration order = flatten data order) and rebound() every
+        value: bounds refitted, topology unchanged -- the host-side form of rt_refit()."""
+        keys = np.ascontiguousarray(keys, self.dtype)
+        per = self.dim * (2 if self.key_is_box else 1)
+        if lib().rtb_tree_set_keys(self._h, _ptr(keys), keys.size // per) != keys.size // per:
+            raise RuntimeError("set_keys: key count differs from the tree's size " + _err())
         return self
 
     def erase_ids(self, ids):

@@ -79,6 +79,8 @@ def ref_lib():
         lib.ref_search_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int,
                                         C.c_void_p, _u32pp, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_double)]
+        lib.ref_tree_set_keys.restype = C.c_int64
+        lib.ref_tree_set_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         lib.ref_search_knn.restype = C.c_int64
         lib.ref_search_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int,
                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
@@ -188,6 +190,15 @@ class RefTree:
         per = self.dim * (2 if self.key_is_box else 1)
         assert keys.size % per == 0
         self.lib.ref_tree_insert(self.h, _ptr(keys), keys.size // per, first_id)
+        return self
+
+    def set_keys(self, keys):
+        """mutate every key in place (iteration order = flatten data order), then rebound() every
+        value (reference README.md:342-347): bounds refitted, topology unchanged"""
+        keys = np.ascontiguousarray(keys, self.dtype)
+        per = self.dim * (2 if self.key_is_box else 1)
+        got = self.lib.ref_tree_set_keys(self.h, _ptr(keys), keys.size // per)
+        assert got == keys.size // per, "set_keys: key count differs from the tree's size"
         return self
 
     def leaf_level(self):

@@ -254,3 +254,26 @@ def test_device_image_file_round_trip_and_corruption(rtb, tmp_path):
             rtb.DeviceImage.load(bad)
     with pytest.raises(RuntimeError):
         rtb.DeviceImage.load(str(tmp_path / "does_not_exist.rtb"))
+
+
+@pytest.mark.parametrize("kind", [4, 5, 2])
+def test_set_keys_rebound_matches_the_reference(rtb, kind):
+    """keys changed in place through the iterators + rebound() for every value: the host library's
+    tree flattens to the same arrays as the reference's after the same mutation"""
+    scalar, dim, is_box, _ = O.KINDS[kind]
+    dt = O.SCALAR_DTYPES[scalar]
+    rng = np.random.default_rng(40 + kind)
+    n = 6000
+    c = rng.random((n, dim))
+    keys = np.stack([c, c + rng.uniform(0, 0.02, (n, dim))], axis=1).astype(dt) if is_box else c.astype(dt)
+    mine, ref = rtb.RTree(kind).insert(keys), O.RefTree(kind).insert(keys)
+    order = mine.flatten()["data"]
+    moved = (keys + rng.normal(0, 0.05, keys.shape)).astype(dt)
+    if is_box:
+        moved = np.sort(moved, axis=1)
+    mine.set_keys(moved[order])
+    ref.set_keys(moved[order])
+    a, b = mine.flatten(), ref.flatten()
+    assert np.array_equal(a["nodes"], b.nodes) and np.array_equal(a["children"], b.children)
+    assert np.array_equal(a["data"], b.data)
+    assert np.array_equal(np.asarray(a["children_bound"]).view(np.uint8), b.bounds.view(np.uint8))
