@@ -243,9 +243,11 @@ int rt_set_stream(rt_tree* tree, void* cuda_stream);
 int rt_get_stats(const rt_tree* tree, rt_stats* out);
 /* Tuning knobs.
  * RT_OPT_PIPELINE_BATCH: a query call with a HOST result and at least two batches' worth of
- *   queries is cut into batches of about this many queries; the copies of neighbouring batches
- *   (H2D of the next, D2H of the previous) run under the traversal of the current one.  The
- *   result is the same CSR as an unpipelined call.  0 = never pipeline.  Default 2 Mi
+ *   queries is cut into batches of about this many queries (long calls: half-size batches at
+ *   both ends, double-size ones in the middle); the copies of neighbouring batches (H2D of the
+ *   next, D2H of the previous) run under the traversal of the current one.  The result is the
+ *   same CSR as an unpipelined call.  Ray calls use batches of twice this size.  0 = never
+ *   pipeline.  Default 1 Mi
  *   (environment override at rt_upload: RTB_PIPELINE_BATCH).                              */
 #define RT_OPT_PIPELINE_BATCH 1u
 /* RT_OPT_QUERY_CHUNK: queries a warp claims at a time (default 4).

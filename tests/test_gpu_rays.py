@@ -117,12 +117,12 @@ def test_pipelined_ray_batches_equal_single_batch(rtb):
     want_t, want_id = ref.search_rays(rays, O.RAY_CLOSEST)
     want_any = ref.search_rays(rays, O.RAY_ANY)
     with rtb.RTree(5).insert(boxes).flatten_device().upload(0) as tree:
-        for batch in (0, 4000, 7001, 20000):
+        for batch in (0, 2000, 3501, 10000):
             tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, batch)
             for _ in range(2):
                 r = np.ascontiguousarray(rays)
                 out = tree.query_rays_raw(r.ctypes.data, len(r), rtb.RT_RAY_CLOSEST, 0)
-                assert tree.stats()["batches"] == (max(1, len(r) // batch) if batch else 1)
+                assert tree.stats()["batches"] == (max(1, len(r) // (2 * batch)) if batch else 1)
                 assert out.n_hit == int((want_id != 0xFFFFFFFF).sum())
                 t, tid = tree.query_rays(rays, rtb.RT_RAY_CLOSEST)
                 assert np.array_equal(t.view(np.uint32), want_t.view(np.uint32)) and np.array_equal(tid, want_id)
