@@ -258,9 +258,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the query path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # stdout carries the ONE JSON line only: libraries that print there (NCCL writes its version
+    # banner with printf when NCCL_DEBUG is set) are sent to stderr until the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the ONE JSON line only
         dist.init_process_group("nccl", device_id=device)
 
     def barrier():
@@ -466,7 +470,10 @@ def main():
             "parity": parity,
             "rays": rays_section,
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     gpu_tree.close()
     if world > 1:
         dist.destroy_process_group()
