@@ -145,12 +145,18 @@ __device__ __forceinline__ uint32_t claim_chunk(const WorkRanges& w, uint32_t ra
   return __shfl_sync(0xFFFFFFFFu, c, 0);
 }
 
-// ascending bitonic sort of one value per lane
-__device__ __forceinline__ uint32_t warp_sort32(uint32_t v, int lane)
+// ascending bitonic sort of one value per lane; only the first `count` lanes hold values, the
+// others RT_INVALID_ID (the largest key): with count <= 8 / 16 the network over the first 8 / 16 lanes
+// already leaves everything in place, so the later merge stages are skipped (count is warp-uniform)
+__device__ __forceinline__ uint32_t warp_sort32(uint32_t v, int lane, uint32_t count = 32u)
 {
 #pragma unroll
   for (int k = 2; k <= 32; k <<= 1)
   {
+    if (k == 16 && count <= 8u)
+      break;
+    if (k == 32 && count <= 16u)
+      break;
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1)
     {

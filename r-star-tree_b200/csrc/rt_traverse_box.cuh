@@ -268,7 +268,7 @@ box_traverse_kernel(const BoxLaunch p)
           {
             uint32_t v = ((uint32_t)lane < count) ? lds_u32(hitbuf + lane * 4u) : RT_INVALID_ID;
             if (p.sorted)
-              v = warp_sort32(v, lane);
+              v = warp_sort32(v, lane, count);
             if ((uint32_t)lane < count)
               p.stash[slab_pos + lane] = v;
             where = (uint32_t)slab_pos;
@@ -289,7 +289,7 @@ box_traverse_kernel(const BoxLaunch p)
         if (buffered)
         {
           uint32_t v = ((uint32_t)lane < count) ? lds_u32(hitbuf + lane * 4u) : RT_INVALID_ID;
-          v = warp_sort32(v, lane);
+          v = warp_sort32(v, lane, count);
           if ((uint32_t)lane < count && (uint32_t)lane < expect)
             p.ids[out_base + lane] = v;
         }
