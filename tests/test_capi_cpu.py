@@ -38,13 +38,16 @@ def test_abi_version_and_struct_sizes(rtb):
     assert C.sizeof(capi.RtHits) == 40
     assert C.sizeof(capi.RtRayResult) == 88
     assert C.sizeof(capi.RtStats) == 72
+    assert C.sizeof(capi.RtKnnResult) == 32
 
 
 def test_header_compiles_as_plain_c(rtb, tmp_path):
     src = tmp_path / "abi.c"
     src.write_text('#include <rtree_b200.h>\n#include <stddef.h>\n'
-                   'int sizes[4] = { sizeof(rt_tree_desc), sizeof(rt_hits), sizeof(rt_ray_result), sizeof(rt_stats) };\n'
-                   'int main(void) { return sizes[0] == 88 && sizes[1] == 40 && sizes[2] == 88 && sizes[3] == 72 ? 0 : 1; }\n')
+                   'int sizes[5] = { sizeof(rt_tree_desc), sizeof(rt_hits), sizeof(rt_ray_result), sizeof(rt_stats),\n'
+                   '                 sizeof(rt_knn_result) };\n'
+                   'int main(void) { return sizes[0] == 88 && sizes[1] == 40 && sizes[2] == 88 && sizes[3] == 72\n'
+                   '                        && sizes[4] == 32 ? 0 : 1; }\n')
     exe = tmp_path / "abi"
     inc = os.path.dirname(rtb.capi.HEADER_PATH)
     assert os.system("/usr/bin/gcc -std=c99 -Wall -Werror -I%s -o %s %s" % (inc, exe, src)) == 0
