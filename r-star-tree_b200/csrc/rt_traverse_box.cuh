@@ -20,11 +20,19 @@
 //
 // Stack.  Per warp in shared memory.  Popping the top G entries and pushing children in
 // lane order keeps the stack sorted by level, hence at most 32 entries per level are
-// ever live: capacity 32 * num_levels, no overflow path needed.
+// ever live: capacity 32 * num_levels, no overflow path needed.  Group g pops index
+// sp - G + g; below index 0 sit G words naming the "null" block rt_upload appends (all
+// slots empty), so a step with fewer than G nodes left needs no activity mask.
+//
+// Work.  Persistent grid; the queries (Morton order after the coherence pass) are cut into
+// one contiguous range per SM and the warps of an SM claim a few queries at a time from
+// their range, stealing from the other ranges at the end (WorkRanges, rt_common.cuh): the
+// 64 warps of an SM walk neighbouring queries and share their nodes in L1.
 //
 // Memory.  Internal levels are a small, hot prefix of the block buffer; they and the
 // leaves stream through L1/L2 via the read-only path (ld.global.nc).  Nothing is written
-// but counts / hit ids.
+// but counts / hit ids.  QUANT (3-D float32 point trees): the same traversal on the
+// quantised image of rt_quant.cuh -- 16 bytes per slot, one integer test per slot.
 //
 // Output.  PASS_COUNT(+STATS): hits per query.  PASS_STASH: hits per query, and lists of
 // at most HIT_BUF hits are sorted in registers (bitonic over the warp) and parked in a
