@@ -71,7 +71,7 @@ box_traverse_kernel(const BoxLaunch p)
   const uint32_t stack_cap = 32u * p.tree.num_levels;
   const uint32_t warp_mem = smem_addr(smem + warp * (HIT_BUF + G + stack_cap));
   const uint32_t stack = warp_mem + (HIT_BUF + G) * 4u;
-#define hitbuf (stack - (HIT_BUF + G) * 4u)
+  constexpr uint32_t HITBUF_BELOW = (HIT_BUF + G) * 4u; // hit buffer = stack - HITBUF_BELOW
   // group g pops the word at stack_pop + 4 * sp, i.e. stack index sp - G + g: with fewer than G
   // nodes left the lower groups read the null node below the stack (a block of empty slots),
   // so popping needs no "is this group active" logic at all
@@ -228,7 +228,7 @@ box_traverse_kernel(const BoxLaunch p)
               if (buffered)
               {
                 if (at < HIT_BUF)
-                  sts_u32(hitbuf + at * 4u, link);
+                  sts_u32(stack - HITBUF_BELOW + at * 4u, link);
               }
               else if (PASS == PASS_WRITE && at < expect)
               {
@@ -274,7 +274,7 @@ box_traverse_kernel(const BoxLaunch p)
           }
           if (slab_left >= count)
           {
-            uint32_t v = ((uint32_t)lane < count) ? lds_u32(hitbuf + lane * 4u) : RT_INVALID_ID;
+            uint32_t v = ((uint32_t)lane < count) ? lds_u32(stack - HITBUF_BELOW + lane * 4u) : RT_INVALID_ID;
             if (p.sorted)
               v = warp_sort32(v, lane, count);
             if ((uint32_t)lane < count)
@@ -296,7 +296,7 @@ box_traverse_kernel(const BoxLaunch p)
       {
         if (buffered)
         {
-          uint32_t v = ((uint32_t)lane < count) ? lds_u32(hitbuf + lane * 4u) : RT_INVALID_ID;
+          uint32_t v = ((uint32_t)lane < count) ? lds_u32(stack - HITBUF_BELOW + lane * 4u) : RT_INVALID_ID;
           v = warp_sort32(v, lane, count);
           if ((uint32_t)lane < count && (uint32_t)lane < expect)
             p.ids[out_base + lane] = v;
@@ -316,7 +316,6 @@ box_traverse_kernel(const BoxLaunch p)
     atomicAdd(p.visit_stats + 1, visits_leaf);
     atomicAdd(p.visit_stats + 3, steps);
   }
-#undef hitbuf
 }
 
 template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS, bool QUANT = false>
