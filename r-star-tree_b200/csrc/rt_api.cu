@@ -613,14 +613,13 @@ int rt_upload(const rt_tree_desc* desc, int device, rt_tree** out)
   t->dev.null_link = (uint32_t)(null_offset / 16);
   t->dev.num_nodes = desc->num_nodes;
   t->dev.num_levels = desc->num_levels;
-  if (desc->scalar == RT_F32 && desc->dim == 3 && desc->width == 8 && desc->key_kind == RT_KEY_POINT
+  if (rtb::quant_supported(desc->scalar, desc->dim, desc->width, desc->key_kind)
       && std::getenv("RTB_NO_QUANT") == nullptr)
   {
-    e = cudaMalloc((void**)&t->d_qblocks, rtb::quant_image_bytes(desc->num_nodes));
+    e = cudaMalloc((void**)&t->d_qblocks, rtb::quant_image_bytes(desc->num_nodes, desc->dim, desc->width));
     if (e != cudaSuccess)
       return cleanup(RT_E_NOMEM, std::string("rt_upload: cudaMalloc(quantised image): ") + cudaGetErrorString(e));
-    e = rtb::build_quant_image(t->dev, desc->level_node_begin[desc->leaf_level], desc->leaf_offset, t->d_qblocks,
-                               t->stream);
+    e = rtb::build_quant_image(t->dev, t->desc, desc->level_node_begin[desc->leaf_level], t->d_qblocks, t->stream);
     if (e != cudaSuccess)
       return cleanup(RT_E_CUDA, std::string("rt_upload: quantised image: ") + cudaGetErrorString(e));
   }
@@ -1418,7 +1417,7 @@ int rt_refit(rt_tree* t, const void* keys, uint64_t n_keys, uint32_t flags)
   if (t->d_qblocks)
   {
     // the quantised image follows the float blocks (the grid is re-derived from the new root bounds)
-    RT_CUDA(rtb::build_quant_image(t->dev, t->levels[t->desc.leaf_level], t->desc.leaf_offset, t->d_qblocks, st));
+    RT_CUDA(rtb::build_quant_image(t->dev, t->desc, t->levels[t->desc.leaf_level], t->d_qblocks, st));
     launches += 2;
   }
   RT_CUDA(cudaEventRecord(ev[EV_TRAVERSE], st));

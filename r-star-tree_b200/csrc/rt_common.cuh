@@ -23,14 +23,14 @@ struct TreeDev
   const unsigned char* blocks; // internal blocks, then (at leaf_offset) leaf blocks
   uint32_t leaf_link_begin;    // leaf_offset / 16
   uint32_t null_link;          // a block past the leaves whose slots are all empty (appended by rt_upload)
-  // Quantised image (rt_quant.cuh; 3-D float32 point-keyed trees with W = 8 only, else NULL): one
-  // 128-byte block per node -- internal nodes first, then from qleaf_link_begin the leaves in the
-  // order of `blocks` -- whose 16-byte slot records hold conservative 15-bit bounds + the link.
+  // Quantised image (rt_quant.cuh; float32 point-keyed trees of the instantiated (dim, width) pairs,
+  // else NULL): one block of W records of dim + 1 words per node -- internal nodes first, then from
+  // qleaf_link_begin the leaves in the order of `blocks` -- holding conservative 15-bit bounds + the link.
   const unsigned char* qblocks;
   const unsigned char* leaf_blocks; // blocks + leaf_offset: the exact records behind the leaf slots
   uint32_t qleaf_link_begin;
   uint32_t qnull_link;
-  float qlo[3], qscale[3];          // the grid: q(v) = clamp(floor((v - qlo) * qscale) + 1, 1, 32767)
+  float qlo[8], qscale[8];          // the grid: q(v) = clamp(floor((v - qlo) * qscale) + 1, 1, 32767)
   uint32_t num_nodes;
   uint32_t num_levels;
 };
@@ -159,11 +159,13 @@ cudaError_t launch_knn_kernel(const KnnLaunch&, uint32_t dim, uint32_t width, ui
 cudaError_t plan_work(const void* kernel, size_t smem, uint64_t n, int forced_grid, cudaStream_t stream,
                       WorkRanges& work, int& grid);
 
-// rt_quant.cu: build the quantised image of a 3-D float32 point-keyed W = 8 tree.  `qblocks` must hold
-// quant_image_bytes(num_nodes) bytes; fills tree.qblocks / leaf_blocks / qleaf_link_begin /
-// qnull_link / qlo / qscale (synchronises the stream once to read the grid back).
-size_t quant_image_bytes(uint32_t num_nodes);
-cudaError_t build_quant_image(TreeDev& tree, uint32_t num_internal, uint64_t leaf_offset, unsigned char* qblocks,
+// rt_quant.cu: the quantised image of a float32 point-keyed tree.  quant_supported(): is there a
+// traversal kernel for it; `qblocks` must hold quant_image_bytes() bytes; build_quant_image() fills
+// tree.qblocks / leaf_blocks / qleaf_link_begin / qnull_link / qlo / qscale (synchronises the stream
+// once to read the grid back).
+bool quant_supported(uint32_t scalar, uint32_t dim, uint32_t width, uint32_t key_kind);
+size_t quant_image_bytes(uint32_t num_nodes, uint32_t dim, uint32_t width);
+cudaError_t build_quant_image(TreeDev& tree, const rt_tree_desc& desc, uint32_t num_internal, unsigned char* qblocks,
                               cudaStream_t stream);
 
 // rt_refit.cu: new keys (flatten data order) into the leaf slots, then all bounds bottom-up

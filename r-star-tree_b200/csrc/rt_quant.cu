@@ -8,31 +8,42 @@ namespace
 {
 struct Grid
 {
-  float lo[3], scale[3];
+  float lo[8], scale[8];
 };
 
-// one warp: the grid spans the bounds of the root's children (= of all keys)
-__global__ void quant_grid_kernel(const unsigned char* blocks, bool root_is_leaf, uint64_t leaf_offset, Grid* grid)
+struct Shape
 {
-  const int lane = threadIdx.x;
-  float lo[3], hi[3];
-  bool valid = false;
-  if (lane < 8)
+  const unsigned char* blocks; // the float image
+  uint64_t leaf_offset;
+  uint32_t internal_stride, leaf_stride, internal_words, leaf_words;
+  uint32_t width, dim, num_nodes, num_internal;
+  uint32_t qstride; // bytes per node in the quantised image (internal and leaf alike)
+};
+
+__device__ __forceinline__ float float_at(const unsigned char* block, uint32_t width, uint32_t words, uint32_t c,
+                                          uint32_t j)
+{
+  return __uint_as_float(*reinterpret_cast<const uint32_t*>(block + block_word_offset(width, words, c, j)));
+}
+
+// one warp: the grid spans the bounds of the root's children (= of all keys)
+__global__ void quant_grid_kernel(Shape s, Grid* grid)
+{
+  const uint32_t lane = threadIdx.x;
+  const bool root_is_leaf = s.num_internal == 0;
+  const unsigned char* block = s.blocks + (root_is_leaf ? s.leaf_offset : 0);
+  const uint32_t words = root_is_leaf ? s.leaf_words : s.internal_words;
+  const bool valid = lane < s.width
+                     && *reinterpret_cast<const uint32_t*>(block + block_word_offset(s.width, words, lane, s.dim))
+                            != RT_INVALID_ID;
+  for (uint32_t d = 0; d < s.dim; ++d)
   {
-    const unsigned char* blk = blocks + (root_is_leaf ? leaf_offset : 0);
-    const uint4 r0 = *reinterpret_cast<const uint4*>(blk + lane * 16);
-    valid = r0.w != RT_INVALID_ID;
-    uint4 r1 = r0;
-    if (!root_is_leaf)
-      r1 = *reinterpret_cast<const uint4*>(blk + 128 + lane * 16);
-    lo[0] = __uint_as_float(r0.x), lo[1] = __uint_as_float(r0.y), lo[2] = __uint_as_float(r0.z);
-    hi[0] = __uint_as_float(r1.x), hi[1] = __uint_as_float(r1.y), hi[2] = __uint_as_float(r1.z);
-  }
-#pragma unroll
-  for (int d = 0; d < 3; ++d)
-  {
-    float l = valid ? lo[d] : __uint_as_float(0x7F800000u);
-    float h = valid ? hi[d] : __uint_as_float(0xFF800000u);
+    float l = __uint_as_float(0x7F800000u), h = __uint_as_float(0xFF800000u);
+    if (valid)
+    {
+      l = float_at(block, s.width, words, lane, d);
+      h = root_is_leaf ? l : float_at(block, s.width, words, lane, s.dim + 1 + d);
+    }
     for (int k = 16; k > 0; k >>= 1)
     {
       l = fminf(l, __shfl_xor_sync(0xFFFFFFFFu, l, k));
@@ -50,61 +61,102 @@ __global__ void quant_grid_kernel(const unsigned char* blocks, bool root_is_leaf
   }
 }
 
-// one thread per (node, slot)
-__global__ void __launch_bounds__(256) quant_build_kernel(const unsigned char* blocks, uint32_t num_nodes,
-                                                          uint32_t num_internal, uint64_t leaf_offset,
-                                                          const Grid* grid, unsigned char* qblocks)
+// one thread per (node, slot); node == num_nodes is the null block
+template <int D>
+__global__ void __launch_bounds__(256) quant_build_kernel(Shape s, const Grid* grid, unsigned char* qblocks)
 {
   const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t node = (uint32_t)(tid >> 3), slot = (uint32_t)(tid & 7);
-  if (node > num_nodes) // node == num_nodes: the null block
+  const uint32_t node = (uint32_t)(tid / s.width), slot = (uint32_t)(tid % s.width);
+  if (node > s.num_nodes)
     return;
-  uint4 out = make_uint4(QUANT_GUARD, QUANT_GUARD, QUANT_GUARD, RT_INVALID_ID); // an empty slot
-  if (node < num_nodes)
+  uint32_t a[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j)
+    a[j] = QUANT_GUARD; // an empty slot: a = 0 in every half
+  uint32_t link = RT_INVALID_ID;
+  if (node < s.num_nodes)
   {
-    const bool leaf = node >= num_internal;
-    const unsigned char* blk = leaf ? blocks + leaf_offset + (uint64_t)(node - num_internal) * 128
-                                    : blocks + (uint64_t)node * 256;
-    const uint4 r0 = *reinterpret_cast<const uint4*>(blk + slot * 16);
-    if (r0.w != RT_INVALID_ID)
+    const bool leaf = node >= s.num_internal;
+    const unsigned char* block = leaf ? s.blocks + s.leaf_offset + (uint64_t)(node - s.num_internal) * s.leaf_stride
+                                      : s.blocks + (uint64_t)node * s.internal_stride;
+    const uint32_t words = leaf ? s.leaf_words : s.internal_words;
+    const uint32_t raw = *reinterpret_cast<const uint32_t*>(block + block_word_offset(s.width, words, slot, D));
+    if (raw != RT_INVALID_ID)
     {
-      uint4 r1 = r0;
-      if (!leaf)
-        r1 = *reinterpret_cast<const uint4*>(blk + 128 + slot * 16);
-      const float lo[3] = { __uint_as_float(r0.x), __uint_as_float(r0.y), __uint_as_float(r0.z) };
-      const float hi[3] = { __uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z) };
-      const float glo[3] = { grid->lo[0], grid->lo[1], grid->lo[2] };
-      const float gscale[3] = { grid->scale[0], grid->scale[1], grid->scale[2] };
-      uint32_t a[3];
-      quant_slot(lo, hi, glo, gscale, a);
-      uint32_t link = r0.w; // leaf entry: the id
+      float lo[D], hi[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+      {
+        lo[d] = float_at(block, s.width, words, slot, d);
+        hi[d] = leaf ? lo[d] : float_at(block, s.width, words, slot, D + 1 + d);
+      }
+      quant_slot<D>(lo, hi, grid->lo, grid->scale, a);
+      link = raw; // leaf entry: the id
       if (!leaf)
       {
-        // child link of the float image (byte offset / 16) -> link of the quantised image
-        const uint32_t leaf_link = (uint32_t)(leaf_offset / 16);
-        link = r0.w < leaf_link ? r0.w / 2                                   // internal: 256 -> 128 bytes
-                                : num_internal * (QUANT_BLOCK / 16) + (r0.w - leaf_link); // leaf: same stride
+        // child link of the float image (byte offset / 16) -> breadth-first node index -> link of
+        // the quantised image, where every node has the same stride
+        const uint64_t offset = (uint64_t)raw * 16u;
+        const uint32_t child = offset < s.leaf_offset
+                                   ? (uint32_t)(offset / s.internal_stride)
+                                   : s.num_internal + (uint32_t)((offset - s.leaf_offset) / s.leaf_stride);
+        link = child * (s.qstride / 16u);
       }
-      out = make_uint4(a[0], a[1], a[2], link);
     }
   }
-  *reinterpret_cast<uint4*>(qblocks + (uint64_t)node * QUANT_BLOCK + slot * 16) = out;
+  unsigned char* out = qblocks + (uint64_t)node * s.qstride;
+#pragma unroll
+  for (int j = 0; j < D; ++j)
+    *reinterpret_cast<uint32_t*>(out + block_word_offset(s.width, D + 1, slot, j)) = a[j];
+  *reinterpret_cast<uint32_t*>(out + block_word_offset(s.width, D + 1, slot, D)) = link;
+}
+
+template <int D>
+void launch_build(const Shape& s, const Grid* grid, unsigned char* qblocks, cudaStream_t stream)
+{
+  const uint64_t threads = ((uint64_t)s.num_nodes + 1) * s.width;
+  quant_build_kernel<D><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(s, grid, qblocks);
 }
 } // namespace
 
-size_t quant_image_bytes(uint32_t num_nodes)
+// the (dim, width) pairs box_traverse_kernel<..., QUANT> is instantiated for (rt_traverse_box.cuh)
+bool quant_supported(uint32_t scalar, uint32_t dim, uint32_t width, uint32_t key_kind)
 {
-  return ((size_t)num_nodes + 1) * QUANT_BLOCK + sizeof(Grid);
+  if (scalar != RT_F32 || key_kind != RT_KEY_POINT)
+    return false;
+  return (dim == 2 && width == 8) || (dim == 3 && width == 8) || (dim == 8 && width == 16);
 }
 
-cudaError_t build_quant_image(TreeDev& tree, uint32_t num_internal, uint64_t leaf_offset, unsigned char* qblocks,
+size_t quant_image_bytes(uint32_t num_nodes, uint32_t dim, uint32_t width)
+{
+  return ((size_t)num_nodes + 1) * rt_block_bytes(width, dim + 1) + sizeof(Grid) + 256;
+}
+
+cudaError_t build_quant_image(TreeDev& tree, const rt_tree_desc& desc, uint32_t num_internal, unsigned char* qblocks,
                               cudaStream_t stream)
 {
-  Grid* d_grid = reinterpret_cast<Grid*>(qblocks + ((size_t)tree.num_nodes + 1) * QUANT_BLOCK);
-  quant_grid_kernel<<<1, 32, 0, stream>>>(tree.blocks, num_internal == 0, leaf_offset, d_grid);
-  const uint64_t threads = ((uint64_t)tree.num_nodes + 1) * 8;
-  quant_build_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(tree.blocks, tree.num_nodes, num_internal,
-                                                                         leaf_offset, d_grid, qblocks);
+  Shape s;
+  s.blocks = tree.blocks;
+  s.leaf_offset = desc.leaf_offset;
+  s.internal_stride = desc.internal_stride;
+  s.leaf_stride = desc.leaf_stride;
+  s.internal_words = rt_record_words(desc.dim, desc.scalar, 1);
+  s.leaf_words = rt_record_words(desc.dim, desc.scalar, 0);
+  s.width = desc.width;
+  s.dim = desc.dim;
+  s.num_nodes = desc.num_nodes;
+  s.num_internal = num_internal;
+  s.qstride = rt_block_bytes(desc.width, desc.dim + 1);
+  const size_t image = ((size_t)desc.num_nodes + 1) * s.qstride;
+  Grid* d_grid = reinterpret_cast<Grid*>(qblocks + (image + 255) / 256 * 256);
+  quant_grid_kernel<<<1, 32, 0, stream>>>(s, d_grid);
+  switch (desc.dim)
+  {
+  case 2: launch_build<2>(s, d_grid, qblocks, stream); break;
+  case 3: launch_build<3>(s, d_grid, qblocks, stream); break;
+  case 8: launch_build<8>(s, d_grid, qblocks, stream); break;
+  default: return cudaErrorInvalidValue;
+  }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess)
     return err;
@@ -113,15 +165,15 @@ cudaError_t build_quant_image(TreeDev& tree, uint32_t num_internal, uint64_t lea
     return err;
   if ((err = cudaStreamSynchronize(stream)) != cudaSuccess)
     return err;
-  for (int d = 0; d < 3; ++d)
+  for (uint32_t d = 0; d < 8; ++d)
   {
-    tree.qlo[d] = h.lo[d];
-    tree.qscale[d] = h.scale[d];
+    tree.qlo[d] = d < desc.dim ? h.lo[d] : 0.0f;
+    tree.qscale[d] = d < desc.dim ? h.scale[d] : 0.0f;
   }
   tree.qblocks = qblocks;
-  tree.leaf_blocks = tree.blocks + leaf_offset;
-  tree.qleaf_link_begin = num_internal * (QUANT_BLOCK / 16);
-  tree.qnull_link = tree.num_nodes * (QUANT_BLOCK / 16);
+  tree.leaf_blocks = tree.blocks + desc.leaf_offset;
+  tree.qleaf_link_begin = num_internal * (s.qstride / 16u);
+  tree.qnull_link = desc.num_nodes * (s.qstride / 16u);
   return cudaSuccess;
 }
 } // namespace rtb

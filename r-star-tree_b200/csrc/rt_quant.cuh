@@ -1,28 +1,31 @@
-// rt_quant.cuh -- the quantised node image of the headline tree kind (3-D float32 points, W = 8).
+// rt_quant.cuh -- the quantised node image of float32 point-keyed trees.
 //
-// The exact traversal reads 256 bytes per internal node (two 128-byte rows of float corners) and
-// spends six FSETP per child.  For this tree kind rt_upload also builds a second image in which
-// EVERY slot of EVERY node -- child bounds of internal nodes and the points of leaves alike -- is one
-// 16-byte record
-//     A0 = G | q(hi_x) | q(hi_y) << 16     A1 = G | n(lo_x) | n(lo_y) << 16
-//     A2 = G | q(hi_z) | n(lo_z) << 16     link (child block / 16, or the leaf entry's id)
+// The exact traversal reads two-corner float records (2 D + 1 words per slot of an internal node:
+// 256 bytes per node in 3-D with W = 8, 1088 bytes in 8-D with W = 16) and spends two FSETP per
+// axis and child.  For float32 point-keyed trees rt_upload also builds a second image in which EVERY
+// slot of EVERY node -- child bounds of internal nodes and the points of leaves alike -- is a record of
+// D + 1 words: 2 D conservative 15-bit grid coordinates, two per word, and the link,
+//     halves  h = q(hi_0) .. q(hi_{D-1}), n(lo_0) .. n(lo_{D-1})          a_j = G | h_2j | h_2j+1 << 16
 // with q(v) = clamp(floor((v - lo_root) * scale) + 1, 1, 32767), n(v) = 32768 - q(v) and guard bits
-// G = 0x80008000.  A query box is brought onto the same grid once,
-//     B0 = q(qlo_x) | q(qlo_y) << 16   B1 = n(qhi_x) | n(qhi_y) << 16   B2 = q(qlo_z) | n(qhi_z) << 16
-// and "all six interval tests pass" is  ((A0-B0) & (A1-B1) & (A2-B2) & G) == G : every half-word
-// difference keeps its guard bit exactly when a >= b, and never borrows from its neighbour.
+// G = 0x80008000 (D odd: the last half-word pairs q(hi_{D-1}) with n(lo_0), and so on -- the list is
+// simply packed in order).  A query box is brought onto the same grid once,
+//     halves  b = q(qlo_0) .. q(qlo_{D-1}), n(qhi_0) .. n(qhi_{D-1})      b_j = b_2j | b_2j+1 << 16
+// and "all 2 D interval tests pass" is  (AND_j (a_j - b_j)) & G == G : every half-word difference
+// keeps its guard bit exactly when a >= b, and never borrows from its neighbour.
 //
 // q is monotone non-decreasing (round-to-nearest subtract and multiply by a non-negative scale,
 // floor, clamp) and the SAME device function quantises node bounds and query bounds, so
 //     hi >= qlo  implies  q(hi) >= q(qlo)      and      lo <= qhi  implies  q(lo) <= q(qhi):
 // the quantised test passes whenever the reference's closed-overlap filter (reference
 // example/sample/sample.cpp:48-54) passes.  It is a CONSERVATIVE filter: internal nodes may be
-// visited that the exact filter would skip (about one grid cell per face: < 1 % more), and leaf
-// slots that pass are candidates which are then tested exactly on the original float record
-// (reference include/RTree/aabb.hpp:206-210).  Hit sets are therefore identical to the exact path.
+// visited that the exact filter would skip (about one grid cell per face), and leaf slots that pass
+// are candidates which are then tested exactly on the original float record (reference
+// include/RTree/aabb.hpp:206-210).  Hit sets are therefore identical to the exact path.
 // Empty slots carry a = 0 in every half (below every b >= 1) and can never pass.  A NaN query
 // bound does not constrain (as in the reference's comparisons): lower bounds map to 1, upper
-// bounds to 32767.  One node is one 128-byte line: half the L1 wavefronts of the exact layout.
+// bounds to 32767.  In 3-D a node is one 128-byte line instead of two; in 8-D (W = 16) 576 bytes
+// instead of 1088.  A point leaf's quantised block has the stride of its float block (D + 1 words
+// per slot in both), so the float record behind a candidate sits at a constant distance.
 #pragma once
 
 #include "rt_common.cuh"
@@ -30,7 +33,6 @@
 namespace rtb
 {
 constexpr uint32_t QUANT_GUARD = 0x80008000u;
-constexpr uint32_t QUANT_BLOCK = 128; // bytes per node in the quantised image (W = 8 slots x 16 bytes)
 
 __device__ __forceinline__ uint32_t quant(float v, float lo, float scale)
 {
@@ -44,41 +46,62 @@ __device__ __forceinline__ uint32_t quant_upper(float v, float lo, float scale)
   return (v != v) ? 32767u : quant(v, lo, scale);
 }
 
-// the three A words of a slot with corners lo / hi
-__device__ __forceinline__ void quant_slot(const float (&lo)[3], const float (&hi)[3], const float (&glo)[3],
-                                           const float (&gscale)[3], uint32_t (&a)[3])
+// 2 D half-words, in order, two per word
+template <int D>
+__device__ __forceinline__ void quant_pack(const uint32_t (&h)[2 * D], uint32_t guard, uint32_t (&w)[D])
 {
-  uint32_t qh[3], nl[3];
 #pragma unroll
-  for (int d = 0; d < 3; ++d)
-  {
-    qh[d] = quant(hi[d], glo[d], gscale[d]);
-    nl[d] = 32768u - quant(lo[d], glo[d], gscale[d]);
-  }
-  a[0] = QUANT_GUARD | qh[0] | (qh[1] << 16);
-  a[1] = QUANT_GUARD | nl[0] | (nl[1] << 16);
-  a[2] = QUANT_GUARD | qh[2] | (nl[2] << 16);
+  for (int j = 0; j < D; ++j)
+    w[j] = guard | h[2 * j] | (h[2 * j + 1] << 16);
 }
 
-// the three B words of a query box
-__device__ __forceinline__ void quant_query(const float (&qlo)[3], const float (&qhi)[3], const float (&glo)[3],
-                                            const float (&gscale)[3], uint32_t (&b)[3])
+// the D words of a slot with corners lo / hi
+template <int D>
+__device__ __forceinline__ void quant_slot(const float (&lo)[D], const float (&hi)[D], const float* glo,
+                                           const float* gscale, uint32_t (&a)[D])
 {
-  uint32_t ql[3], nh[3];
+  uint32_t h[2 * D];
 #pragma unroll
-  for (int d = 0; d < 3; ++d)
+  for (int d = 0; d < D; ++d)
   {
-    ql[d] = quant(qlo[d], glo[d], gscale[d]);
-    nh[d] = 32768u - quant_upper(qhi[d], glo[d], gscale[d]);
+    h[d] = quant(hi[d], glo[d], gscale[d]);
+    h[D + d] = 32768u - quant(lo[d], glo[d], gscale[d]);
   }
-  b[0] = ql[0] | (ql[1] << 16);
-  b[1] = nh[0] | (nh[1] << 16);
-  b[2] = ql[2] | (nh[2] << 16);
+  quant_pack<D>(h, QUANT_GUARD, a);
 }
 
-__device__ __forceinline__ bool quant_pass(const uint4& r, const uint32_t (&b)[3])
+// the D words of a query box
+template <int D>
+__device__ __forceinline__ void quant_query(const float (&qlo)[D], const float (&qhi)[D], const float* glo,
+                                            const float* gscale, uint32_t (&b)[D])
 {
-  const uint32_t t = (r.x - b[0]) & (r.y - b[1]) & (r.z - b[2]);
+  uint32_t h[2 * D];
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+  {
+    h[d] = quant(qlo[d], glo[d], gscale[d]);
+    h[D + d] = 32768u - quant_upper(qhi[d], glo[d], gscale[d]);
+  }
+  quant_pack<D>(h, 0u, b);
+}
+
+template <int D>
+__device__ __forceinline__ bool quant_pass(const uint32_t* a, const uint32_t (&b)[D])
+{
+  uint32_t t = a[0] - b[0];
+#pragma unroll
+  for (int j = 1; j < D; ++j)
+    t &= a[j] - b[j];
   return (t & QUANT_GUARD) == QUANT_GUARD;
+}
+
+// byte offset of word j of slot c in a block of `words`-word records (layout: include/rtree_b200.h)
+__host__ __device__ __forceinline__ uint32_t block_word_offset(uint32_t width, uint32_t words, uint32_t c, uint32_t j)
+{
+  const uint32_t full = words / 4, r = words % 4;
+  if (j < 4 * full)
+    return (j / 4) * width * 16 + c * 16 + (j % 4) * 4;
+  const uint32_t tail = r == 1 ? 4u : (r == 2 ? 8u : 16u);
+  return full * width * 16 + c * tail + (j - 4 * full) * 4;
 }
 } // namespace rtb

@@ -55,8 +55,8 @@ template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS, b
 __global__ void __launch_bounds__(TRAVERSE_THREADS)
 box_traverse_kernel(const BoxLaunch p)
 {
-  static_assert(!QUANT || (std::is_same<S, float>::value && D == 3 && W == 8 && !BOXKEY && PASS != PASS_COUNT_STATS),
-                "the quantised image exists for 3-D float32 point trees with 8-wide blocks");
+  static_assert(!QUANT || (std::is_same<S, float>::value && !BOXKEY && PASS != PASS_COUNT_STATS),
+                "the quantised image exists for float32 point-keyed trees");
   constexpr int G = 32 / W;
   extern __shared__ uint32_t smem[];
 
@@ -123,13 +123,9 @@ box_traverse_kernel(const BoxLaunch p)
         qhi[d] = __ldg(queries + qi * (2 * D) + D + d);
       }
 
-      uint32_t qb[3] = { 0u, 0u, 0u }; // the query on the quantisation grid
+      uint32_t qb[D]; // the query on the quantisation grid (QUANT)
       if constexpr (QUANT)
-      {
-        const float glo[3] = { p.tree.qlo[0], p.tree.qlo[1], p.tree.qlo[2] };
-        const float gscale[3] = { p.tree.qscale[0], p.tree.qscale[1], p.tree.qscale[2] };
-        quant_query(qlo, qhi, glo, gscale, qb);
-      }
+        quant_query<D>(qlo, qhi, p.tree.qlo, p.tree.qscale, qb);
 
       unsigned long long out_base = 0;
       uint32_t expect = 0;
@@ -158,9 +154,11 @@ box_traverse_kernel(const BoxLaunch p)
         bool hit;
         if constexpr (QUANT)
         {
-          const uint4 r = __ldg(reinterpret_cast<const uint4*>(lane_blocks + (unsigned long long)node * 16u));
-          link = r.w;
-          hit = quant_pass(r, qb); // empty slots never pass
+          using Rec = Record<D + 1, W>;
+          uint32_t w[Rec::PADDED];
+          Rec::load(lane_blocks + (unsigned long long)node * 16u, slot, w);
+          link = w[D];
+          hit = quant_pass<D>(w, qb); // empty slots never pass
         }
         else
         {
@@ -212,11 +210,33 @@ box_traverse_kernel(const BoxLaunch p)
             // candidates of the quantised test: the reference's exact test on the float record
             if (leaf_hit)
             {
-              const uint4 e = __ldg(reinterpret_cast<const uint4*>(
-                  lane_blocks + leaf_delta + (unsigned long long)(node - leaf_link_begin) * 16u));
-              const float x = __uint_as_float(e.x), y = __uint_as_float(e.y), z = __uint_as_float(e.z);
-              leaf_hit = !(x < qlo[0]) && !(x > qhi[0]) && !(y < qlo[1]) && !(y > qhi[1]) && !(z < qlo[2])
-                         && !(z > qhi[2]);
+              // the float block of a point leaf has the stride of its quantised block
+              using Key = Record<D + 1, W>;
+              uint32_t kw[Key::PADDED];
+              Key::load(lane_blocks + leaf_delta + (unsigned long long)(node - leaf_link_begin) * 16u, slot, kw);
+              S klo[D];
+#pragma unroll
+              for (int d = 0; d < D; ++d)
+                klo[d] = __uint_as_float(kw[d]);
+              if constexpr (D == 3)
+              {
+                // (written out: the loop form below costs ptxas 8 more registers in the 3-D kernel)
+                leaf_hit = !(klo[0] < qlo[0]) && !(klo[0] > qhi[0]) && !(klo[1] < qlo[1]) && !(klo[1] > qhi[1])
+                           && !(klo[2] < qlo[2]) && !(klo[2] > qhi[2]);
+              }
+              else
+              {
+                bool inside = true;
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+                {
+                  // wide queries are re-read (an L1 hit) rather than held in 2 D registers all along
+                  const S lo_d = D > 3 ? __ldg(queries + qi * (2 * D) + d) : qlo[d];
+                  const S hi_d = D > 3 ? __ldg(queries + qi * (2 * D) + D + d) : qhi[d];
+                  inside = inside && !(klo[d] < lo_d) && !(klo[d] > hi_d);
+                }
+                leaf_hit = inside;
+              }
             }
             m_hits = __ballot_sync(0xFFFFFFFFu, leaf_hit);
           }
@@ -321,7 +341,9 @@ box_traverse_kernel(const BoxLaunch p)
 template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS, bool QUANT = false>
 cudaError_t launch_box_pass(const BoxLaunch& p)
 {
-  constexpr bool CAN_QUANT = std::is_same<S, float>::value && D == 3 && W == 8 && !BOXKEY && PASS != PASS_COUNT_STATS;
+  // the (dim, width) pairs of quant_supported() in rt_quant.cu
+  constexpr bool CAN_QUANT = std::is_same<S, float>::value && !BOXKEY && PASS != PASS_COUNT_STATS
+                             && ((D == 2 && W == 8) || (D == 3 && W == 8) || (D == 8 && W == 16));
   if constexpr (CAN_QUANT && !QUANT)
   {
     if (p.tree.qblocks != nullptr)

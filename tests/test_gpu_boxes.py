@@ -290,16 +290,22 @@ def _boundary_queries(pts, rng, n):
 
 QUANT_CASES = ["uniform", "flat_axis", "huge_range", "tiny_range", "negative_denormal", "single_leaf",
                "single_leaf_extreme", "duplicates"]
+QUANT_KINDS = {4: QUANT_CASES, 3: ["uniform", "flat_axis", "tiny_range", "single_leaf_extreme"],
+               6: ["uniform", "flat_axis", "tiny_range", "single_leaf", "duplicates"]}
 
 
-@pytest.mark.parametrize("case", QUANT_CASES)
-def test_quantised_image_gives_the_exact_hit_sets(rtb, case):
-    """3-D float32 point trees are traversed on a quantised image (conservative 15-bit bounds, leaf
-    candidates confirmed on the float records): hit lists must equal the float-block path and the
-    reference's search() bit for bit, also where quantisation is at its worst"""
-    rng = np.random.default_rng(700 + QUANT_CASES.index(case))
-    n = 40000
-    pts = rng.random((n, 3)).astype(np.float32)
+@pytest.mark.parametrize("kind,case", [(k, c) for k, cases in QUANT_KINDS.items() for c in cases])
+def test_quantised_image_gives_the_exact_hit_sets(rtb, kind, case):
+    """float32 point trees (3-D and 2-D with 8-wide blocks, 8-D with 16-wide ones) are traversed on a
+    quantised image (conservative 15-bit bounds, leaf candidates confirmed on the float records): hit
+    lists must equal the float-block path and the reference's search() bit for bit, also where
+    quantisation is at its worst"""
+    _, dim, _, _ = O.KINDS[kind]
+    rng = np.random.default_rng(700 + QUANT_CASES.index(case) + 50 * kind)
+    n = 40000 if dim <= 3 else 25000
+    pts = rng.random((n, dim)).astype(np.float32)
+    if dim == 8:
+        pts = (rng.random((64, dim))[rng.integers(0, 64, n)] + rng.normal(0, 0.02, (n, dim))).astype(np.float32)
     if case == "flat_axis":
         pts[:, 1] = np.float32(0.25)                       # zero extent on one axis
     elif case == "huge_range":
@@ -315,33 +321,36 @@ def test_quantised_image_gives_the_exact_hit_sets(rtb, case):
         pts = pts[:6]
     elif case == "single_leaf_extreme":
         pts = pts[:6]
-        pts[0] = [3e38, -3e38, 3e38]                       # root extent overflows to +inf: scale 0 on every axis
-        pts[1] = [-3e38, 3e38, -3e38]
+        pts[0] = np.where(np.arange(dim) % 2 == 0, 3e38, -3e38)   # root extent overflows to +inf: scale 0
+        pts[1] = -pts[0]
     elif case == "duplicates":
         pts = pts[rng.integers(0, 50, n)]                  # 50 distinct points, long equal runs
     with np.errstate(over="ignore", invalid="ignore"):
         span = pts.max(axis=0) - pts.min(axis=0)
         c = pts[rng.integers(0, len(pts), 3000)]
-        h = (np.where(np.isfinite(span), span, np.float32(1e30)) * np.float32(0.02)).astype(np.float32)
+        width = 0.02 if dim <= 3 else 0.12
+        h = (np.where(np.isfinite(span), span, np.float32(1e30)) * np.float32(width)).astype(np.float32)
         q = np.concatenate([
             np.stack([c - h, c + h], axis=1).astype(np.float32),
             _boundary_queries(pts, rng, 3000),
             np.stack([c, c], axis=1),                                     # zero-size boxes on data points
             np.stack([c + h, c - h], axis=1).astype(np.float32)[:200],    # inverted
         ])
-    special = np.zeros((8, 2, 3), np.float32)
-    special[0] = [[-np.inf] * 3, [np.inf] * 3]
-    special[1] = [[np.nan] * 3, [np.nan] * 3]
+    special = np.zeros((8, 2, dim), np.float32)
+    special[0] = [[-np.inf] * dim, [np.inf] * dim]
+    special[1] = [[np.nan] * dim, [np.nan] * dim]
     special[2] = [pts.min(axis=0), pts.max(axis=0)]                       # exactly the root box
-    special[3] = [pts.max(axis=0), [np.inf] * 3]                          # touches the root box in one corner
-    special[4] = [[-np.inf] * 3, pts.min(axis=0)]
-    special[5] = [[np.nan, -np.inf, pts[0, 2]], [np.inf, np.nan, pts[0, 2]]]
+    special[3] = [pts.max(axis=0), [np.inf] * dim]                        # touches the root box in one corner
+    special[4] = [[-np.inf] * dim, pts.min(axis=0)]
+    special[5] = [[-np.inf] * dim, [np.inf] * dim]
+    special[5][0, 0], special[5][1, 1] = np.nan, np.nan
+    special[5][:, dim - 1] = pts[0, dim - 1]                              # NaN / inf bounds + a zero-width axis
     special[6] = [pts.max(axis=0) + np.float32(1.0), pts.max(axis=0) + np.float32(2.0)]   # outside
-    special[7] = [[-3e38] * 3, [3e38] * 3]
+    special[7] = [[-3e38] * dim, [3e38] * dim]
     q = np.concatenate([q, special])
-    want = O.RefTree(4).insert(pts).search_boxes(q)
+    want = O.RefTree(kind).insert(pts).search_boxes(q)
     assert want[1].size > 0
-    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+    with rtb.RTree(kind).insert(pts).flatten_device().upload(0) as tree:
         for flags in (0, rtb.RT_NO_REORDER, rtb.RT_UNSORTED, rtb.RT_COUNT_ONLY):
             got = {}
             for quantised in (1, 0):
