@@ -372,3 +372,31 @@ def test_reloaded_image_answers_like_the_original(rtb, tmp_path):
     image.save(path)
     with image.upload(0) as a, rtb.DeviceImage.load(path).upload(0) as b:
         assert csr_equal(a.query_boxes(q), b.query_boxes(q))
+
+
+def test_heavy_hit_lists_at_scale(rtb):
+    """every list far beyond the 32-id stash path (~300 hits per query, 100 k queries, 30 M hits): the
+    second traversal writes them, the segment sort orders them, pipelined or not; a sample is checked
+    against the reference's search(), the whole batch through sortedness and the count-only totals"""
+    n, nq = 1_000_000, 100_000
+    pts = rtb.workloads.uniform_points(n, seed=31)
+    q = rtb.workloads.cube_queries(nq, n, seed=32, hits_per_query=300.0)
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+        tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, 0)
+        off, ids = tree.query_boxes(q)
+        assert tree.stats()["deferred_queries"] > 0.99 * nq
+        tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, 10_000)
+        off2, ids2 = tree.query_boxes(q)
+        assert tree.stats()["batches"] > 2
+        assert np.array_equal(off, off2) and np.array_equal(ids, ids2)
+        coff, _ = tree.query_boxes(q, flags=rtb.RT_COUNT_ONLY)
+        assert np.array_equal(coff, off)
+    counts = np.diff(off.astype(np.int64))
+    assert 250 < counts.mean() < 350 and ids.size == int(off[-1])
+    # ascending inside every segment: a descent can only sit on a segment boundary
+    descents = np.nonzero(np.diff(ids.astype(np.int64)) < 0)[0] + 1
+    assert np.all(np.isin(descents, off[1:-1].astype(np.int64)))
+    sample = np.random.default_rng(3).integers(0, nq, 400)
+    want = O.RefTree(4).insert(pts).search_boxes(q[sample])
+    for k, qi in enumerate(sample):
+        assert np.array_equal(ids[off[qi]:off[qi + 1]], want[1][want[0][k]:want[0][k + 1]])
