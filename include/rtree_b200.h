@@ -77,6 +77,11 @@ extern "C" {
 #define RT_COUNT_ONLY 0x8u        /* fill offsets / total only, no ids                    */
 #define RT_COLLECT_VISITS 0x10u   /* also count node visits (rt_stats), slower            */
 #define RT_NO_REORDER 0x20u       /* process queries in input order (no coherence pass)   */
+#define RT_ANY_HIT 0x40u          /* rt_query_boxes: stop each query at its first hit -- the
+                                     functor-returns-true abort of reference rtree.hpp:994-997.
+                                     Implies RT_COUNT_ONLY; offsets[q+1] - offsets[q] is 0 or 1
+                                     ("does the box hit anything"; which hit came first depends
+                                     on the traversal order and is not reported)            */
 
 /* An id slot that holds no entry.  Ids / value counts must stay below it.            */
 #define RT_INVALID_ID 0xFFFFFFFFu

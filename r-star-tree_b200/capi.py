@@ -21,7 +21,7 @@ RT_MEM_HOST, RT_MEM_DEVICE = 0, 1
 RT_POINT_IN_BOX, RT_INTERSECTS, RT_CONTAINS = 0, 1, 2
 RT_RAY_ALL_HITS, RT_RAY_CLOSEST, RT_RAY_ANY = 0, 1, 2
 RT_QUERIES_ON_DEVICE, RT_RESULT_ON_DEVICE, RT_UNSORTED = 0x1, 0x2, 0x4
-RT_COUNT_ONLY, RT_COLLECT_VISITS, RT_NO_REORDER = 0x8, 0x10, 0x20
+RT_COUNT_ONLY, RT_COLLECT_VISITS, RT_NO_REORDER, RT_ANY_HIT = 0x8, 0x10, 0x20, 0x40
 RT_INVALID_ID = 0xFFFFFFFF
 RT_OPT_PIPELINE_BATCH, RT_OPT_QUERY_CHUNK, RT_OPT_WORK_RANGES, RT_OPT_TRAVERSE_GRID = 1, 2, 3, 4
 RT_OPT_QUANTISED = 5
@@ -211,7 +211,7 @@ class DeviceTree:
         flags &= ~(RT_QUERIES_ON_DEVICE | RT_RESULT_ON_DEVICE)
         out = self.query_boxes_raw(q.ctypes.data, len(q), mode, flags)
         offsets = _host_array(out.offsets, out.n_queries + 1, np.uint64)
-        ids = _host_array(out.ids, 0 if flags & RT_COUNT_ONLY else out.total, np.uint32)
+        ids = _host_array(out.ids, 0 if flags & (RT_COUNT_ONLY | RT_ANY_HIT) else out.total, np.uint32)
         return offsets, ids
 
     def refit(self, keys):

@@ -293,7 +293,7 @@ struct BoxCall
 {
   rtb::box_launch_fn launch;
   size_t query_stride; // bytes per query
-  bool on_device, keep_on_device, count_only, collect, sorted, reorder, two_pass, pipelined;
+  bool on_device, keep_on_device, count_only, collect, sorted, reorder, two_pass, pipelined, any_hit;
 };
 
 struct Batch
@@ -420,6 +420,7 @@ int box_issue_count(rt_tree* t, const BoxCall& c, Batch& b)
   L.grid = t->traverse_grid ? t->traverse_grid : (c.pipelined ? -1 : 0);
   L.visit_stats = dc->visits;
   L.sorted = c.sorted ? 1u : 0u;
+  L.stop_at_first = c.any_hit ? 1u : 0u;
   L.stream = st;
   L.pass = c.two_pass ? (c.collect ? rtb::PASS_COUNT_STATS : rtb::PASS_COUNT) : rtb::PASS_STASH;
   if (n > 0)
@@ -737,7 +738,11 @@ int rt_query_boxes(rt_tree* t, const void* boxes, uint64_t n, uint32_t mode, uin
   c.query_stride = (size_t)2 * t->desc.dim * (t->desc.scalar == RT_F64 ? 8u : 4u);
   c.on_device = (flags & RT_QUERIES_ON_DEVICE) != 0;
   c.keep_on_device = (flags & RT_RESULT_ON_DEVICE) != 0;
-  c.count_only = (flags & RT_COUNT_ONLY) != 0;
+  const bool any_hit = (flags & RT_ANY_HIT) != 0;
+  if (any_hit && (flags & RT_COLLECT_VISITS) != 0)
+    return fail(RT_E_INVALID, "rt_query_boxes: RT_ANY_HIT cannot be combined with RT_COLLECT_VISITS");
+  c.count_only = (flags & RT_COUNT_ONLY) != 0 || any_hit;
+  c.any_hit = any_hit;
   c.collect = (flags & RT_COLLECT_VISITS) != 0;
   c.sorted = (flags & RT_UNSORTED) == 0;
   c.reorder = (flags & RT_NO_REORDER) == 0;

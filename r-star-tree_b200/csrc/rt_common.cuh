@@ -96,6 +96,7 @@ struct BoxLaunch
   WorkRanges work;                  // cursors = MAX_WORK_RANGES entries; the rest is set by the launcher
   unsigned long long* visit_stats;  // [2] internal / leaf visits (COUNT_STATS)
   uint32_t sorted;                  // 0: keep traversal order
+  uint32_t stop_at_first;           // PASS_COUNT: abort a query at its first hit (RT_ANY_HIT): counts are 0 / 1
   int grid;                         // 0: fill the GPU; > 0: exactly; < 0: fill, less -grid CTAs per SM
   cudaStream_t stream;
 };

@@ -257,6 +257,13 @@ box_traverse_kernel(const BoxLaunch p)
             }
           }
           count += __popc(m_hits);
+          if (PASS == PASS_COUNT && p.stop_at_first && count != 0)
+          {
+            // the functor-returns-true abort of reference rtree.hpp:994-997: which hit came first
+            // depends on the traversal order, "there is one" does not
+            count = 1;
+            sp4 = 0;
+          }
         }
         __syncwarp();
       }

@@ -400,3 +400,31 @@ def test_heavy_hit_lists_at_scale(rtb):
     want = O.RefTree(4).insert(pts).search_boxes(q[sample])
     for k, qi in enumerate(sample):
         assert np.array_equal(ids[off[qi]:off[qi + 1]], want[1][want[0][k]:want[0][k + 1]])
+
+
+@pytest.mark.parametrize("kind", [4, 5, 2, 6])
+def test_any_hit_is_the_abort_semantics(rtb, kind):
+    """RT_ANY_HIT stops a query at its first hit (functor returns true, reference rtree.hpp:994-997):
+    the per-query boolean equals "the reference's search() delivered at least one value", on the
+    quantised and the float path, pipelined or not"""
+    scalar, dim, is_box, _ = O.KINDS[kind]
+    dt = O.SCALAR_DTYPES[scalar]
+    rng = np.random.default_rng(300 + kind)
+    n, nq = 30000, 12000
+    c = rng.random((n, dim))
+    keys = np.stack([c, c + rng.uniform(0, 0.01, (n, dim))], axis=1).astype(dt) if is_box else c.astype(dt)
+    qc = rng.uniform(-0.3, 1.3, (nq, dim))                       # a good share of the boxes hit nothing
+    qh = 0.5 * (2.0 / n) ** (1.0 / dim) * rng.uniform(0.2, 2.0, (nq, 1))
+    q = np.stack([qc - qh, qc + qh], axis=1).astype(dt)
+    mode = rtb.RT_INTERSECTS if is_box else rtb.RT_POINT_IN_BOX
+    want = np.diff(O.RefTree(kind).insert(keys).search_boxes(q, mode)[0].astype(np.int64)) > 0
+    assert 0.1 < want.mean() < 0.9
+    with rtb.RTree(kind).insert(keys).flatten_device().upload(0) as tree:
+        for quantised in (1, 0):
+            tree.set_option(rtb.RT_OPT_QUANTISED, quantised)
+            for batch in (0, 2500):
+                tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, batch)
+                off, ids = tree.query_boxes(q, mode, rtb.RT_ANY_HIT)
+                assert ids.size == 0 and np.array_equal(np.diff(off.astype(np.int64)), want.astype(np.int64))
+        with pytest.raises(rtb.RtError):
+            tree.query_boxes(q, mode, rtb.RT_ANY_HIT | rtb.RT_COLLECT_VISITS)
