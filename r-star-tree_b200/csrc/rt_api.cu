@@ -158,6 +158,8 @@ struct Slot
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   unsigned long long stash_wanted = 0; // pool size the last batch on this slot would have needed
+  uint32_t stash_slab = rtb::STASH_SLAB; // slab size for the next batch (grows with the lists seen)
+  unsigned long long last_total = 0, last_n = 0; // hits / queries of the last batch on this slot
 
   void release()
   {
@@ -339,8 +341,15 @@ int box_issue_count(rt_tree* t, const BoxCall& c, Batch& b)
     RT_CUDA(s.d_deferred.reserve((size_t)(n + 1) * sizeof(uint32_t)));
     // pool: what the previous batch needed (+25%), else ~12 ids per query; never more than a
     // quarter of the free memory, never more than 32-bit positions can address
+    // (a batch whose long lists were deferred used little of the pool: also allow for the hits seen,
+    // scaled to this batch, plus the quarter slab a warp may leave unused)
     unsigned long long want = s.stash_wanted ? s.stash_wanted + s.stash_wanted / 4 : n * 12ull;
-    want += 4ull * rtb::STASH_SLAB * 1024;
+    if (s.last_n)
+    {
+      const unsigned long long by_hits = (unsigned long long)((double)s.last_total / (double)s.last_n * (double)n * 1.5);
+      want = want > by_hits ? want : by_hits;
+    }
+    want += 4ull * s.stash_slab * 1024;
     if (want > 0xFFFFF000ull)
       want = 0xFFFFF000ull;
     const unsigned long long have = s.d_stash.cap / sizeof(uint32_t);
@@ -409,6 +418,7 @@ int box_issue_count(rt_tree* t, const BoxCall& c, Batch& b)
   L.stash = s.d_stash.as<uint32_t>();
   L.stash_pos = s.d_stash_pos.as<uint32_t>();
   L.stash_capacity = stash_capacity;
+  L.stash_slab = s.stash_slab;
   L.stash_cursor = &dc->stash_cursor;
   L.deferred_list = s.d_deferred.as<uint32_t>();
   L.deferred_count = &dc->deferred;
@@ -459,7 +469,18 @@ int box_issue_write(rt_tree* t, const BoxCall& c, Batch& b, unsigned long long b
   Counters* dc = s.d_counters.as<Counters>();
   const unsigned long long total = b.hc.total;
   if (!c.two_pass)
+  {
     s.stash_wanted = b.hc.stash_cursor;
+    // slab size for the next batch on this slot: room for lists 16 times the average, so that the
+    // long ones spill into the stash instead of costing a second traversal
+    const unsigned long long average = n ? total / n : 0;
+    uint32_t slab = rtb::STASH_SLAB;
+    while (slab < rtb::STASH_SLAB_MAX && slab < 16 * average)
+      slab *= 2;
+    s.stash_slab = slab;
+    s.last_total = total;
+    s.last_n = n;
+  }
   rtb::BoxLaunch& L = b.L;
 
   RT_CUDA(cudaEventRecord(b.ev[EV_WRITE], st));
@@ -490,11 +511,12 @@ int box_issue_write(rt_tree* t, const BoxCall& c, Batch& b, unsigned long long b
       L.ids = s.d_ids.as<uint32_t>();
       RT_CUDA(c.launch(L));
       ++b.launches;
-      if (c.sorted)
-        RT_CUDA(rtb::launch_sort_segments(s.d_big.as<uint32_t>(), &dc->big, (uint32_t)L.n,
-                                          s.d_offsets.as<unsigned long long>(), s.d_ids.as<uint32_t>(), st,
-                                          &b.launches));
     }
+    // long lists -- spilled into the stash by the first traversal, or written by the second -- are sorted here
+    if (c.sorted && (second || b.hc.big > 0))
+      RT_CUDA(rtb::launch_sort_segments(s.d_big.as<uint32_t>(), &dc->big, (uint32_t)n,
+                                        s.d_offsets.as<unsigned long long>(), s.d_ids.as<uint32_t>(), st,
+                                        &b.launches));
   }
   RT_CUDA(cudaEventRecord(b.ev[EV_FINISH], st));
 

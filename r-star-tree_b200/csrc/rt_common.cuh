@@ -45,7 +45,8 @@ enum : uint32_t
 };
 
 constexpr uint32_t HIT_BUF = 32;        // per-warp hit buffer (one id per lane)
-constexpr uint32_t STASH_SLAB = 512;    // ids a warp reserves from the stash per atomic
+constexpr uint32_t STASH_SLAB = 512;    // ids a warp reserves from the stash per atomic (smallest slab)
+constexpr uint32_t STASH_SLAB_MAX = 16384;
 constexpr uint32_t NO_STASH = 0xFFFFFFFFu;
 constexpr int TRAVERSE_THREADS = 256;   // 8 warps per CTA
 constexpr uint32_t QUERY_CHUNK = 4;     // queries a warp claims per atomic (default)
@@ -88,10 +89,11 @@ struct BoxLaunch
   uint32_t* stash;                  // stash pool  (STASH)
   uint32_t* stash_pos;              // [n_total] position in the pool or NO_STASH (STASH)
   unsigned long long stash_capacity;
+  uint32_t stash_slab;              // ids per slab: a list of up to this many ids can be stashed
   unsigned long long* stash_cursor; // device counter
   uint32_t* deferred_list;          // queries that need PASS_WRITE (STASH)
   uint32_t* deferred_count;
-  uint32_t* big_list;               // queries whose list must be sorted afterwards (WRITE)
+  uint32_t* big_list;               // queries whose list must be sorted afterwards (STASH spills, WRITE)
   uint32_t* big_count;
   WorkRanges work;                  // cursors = MAX_WORK_RANGES entries; the rest is set by the launcher
   unsigned long long* visit_stats;  // [2] internal / leaf visits (COUNT_STATS)

@@ -49,6 +49,20 @@
 namespace rtb
 {
 
+// a fresh slab of the stash pool for this warp (warp-uniform); none left: slab_left = 0, and the
+// queries that needed one are answered by the second traversal
+__device__ __forceinline__ void claim_stash_slab(const BoxLaunch& p, int lane, unsigned long long& slab_pos,
+                                                 uint32_t& slab_left)
+{
+  unsigned long long got = 0;
+  if (lane == 0)
+    got = atomicAdd(p.stash_cursor, (unsigned long long)p.stash_slab);
+  got = __shfl_sync(0xFFFFFFFFu, got, 0);
+  const bool ok = got + p.stash_slab <= p.stash_capacity;
+  slab_pos = ok ? got : slab_pos;
+  slab_left = ok ? p.stash_slab : 0u;
+}
+
 // QUANT: traverse the quantised image (rt_quant.cuh) -- one 16-byte record per slot, one integer
 // test for internal children and leaf points alike, leaf candidates confirmed on the float record.
 template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS, bool QUANT = false>
@@ -137,6 +151,10 @@ box_traverse_kernel(const BoxLaunch p)
         buffered = p.sorted && expect <= HIT_BUF;
       }
 
+      // PASS_STASH: every query starts with at least a quarter slab of room in the warp's slab (and
+      // never less than the hit buffer), so lists up to that length are stashed without further ado
+      if (PASS == PASS_STASH && slab_left < max(HIT_BUF, p.stash_slab / 4))
+        claim_stash_slab(p, lane, slab_pos, slab_left);
       uint32_t count = 0;
       uint32_t sp4 = 4u; // bytes on the stack (kept warp-uniform: it only ever sees ballots)
       if (lane == 0)
@@ -249,6 +267,9 @@ box_traverse_kernel(const BoxLaunch p)
               {
                 if (at < HIT_BUF)
                   sts_u32(stack - HITBUF_BELOW + at * 4u, link);
+                else if (PASS == PASS_STASH && at < slab_left)
+                  p.stash[slab_pos + at] = link; // beyond the hit buffer: straight into the warp's slab,
+                                                 // at its final place there (sorted after the gather)
               }
               else if (PASS == PASS_WRITE && at < expect)
               {
@@ -283,22 +304,6 @@ box_traverse_kernel(const BoxLaunch p)
         }
         else if (count <= HIT_BUF)
         {
-          if (slab_left < count)
-          {
-            unsigned long long got = 0;
-            if (lane == 0)
-              got = atomicAdd(p.stash_cursor, (unsigned long long)STASH_SLAB);
-            got = __shfl_sync(0xFFFFFFFFu, got, 0);
-            if (got + STASH_SLAB <= p.stash_capacity)
-            {
-              slab_pos = got;
-              slab_left = STASH_SLAB;
-            }
-            else
-            {
-              slab_left = 0; // pool exhausted: this and later queries are deferred
-            }
-          }
           if (slab_left >= count)
           {
             uint32_t v = ((uint32_t)lane < count) ? lds_u32(stack - HITBUF_BELOW + lane * 4u) : RT_INVALID_ID;
@@ -310,6 +315,17 @@ box_traverse_kernel(const BoxLaunch p)
             slab_pos += count;
             slab_left -= count;
           }
+        }
+        else if (count <= slab_left)
+        {
+          // a list that outgrew the hit buffer but not the slab: ids HIT_BUF.. are in the slab
+          // already (every one of them had at < slab_left), the first HIT_BUF join them
+          p.stash[slab_pos + lane] = lds_u32(stack - HITBUF_BELOW + lane * 4u);
+          where = (uint32_t)slab_pos;
+          slab_pos += count;
+          slab_left -= count;
+          if (p.sorted && lane == 0)
+            p.big_list[atomicAdd(p.big_count, 1u)] = (uint32_t)qi; // sorted after the gather
         }
         if (lane == 0)
         {
