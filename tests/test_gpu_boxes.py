@@ -433,3 +433,27 @@ def test_any_hit_is_the_abort_semantics(rtb, kind):
                 assert ids.size == 0 and np.array_equal(np.diff(off.astype(np.int64)), want.astype(np.int64))
         with pytest.raises(rtb.RtError):
             tree.query_boxes(q, mode, rtb.RT_ANY_HIT | rtb.RT_COLLECT_VISITS)
+
+
+@pytest.mark.parametrize("kind,dim", [(4, 3), (3, 2)])
+def test_float_lattice_known_answer(rtb, kind, dim):
+    """the reference's Flatten known-answer test (test/rtree.cpp:410-467: a closed range over integer
+    points returns exactly min..max) lifted to float32 lattices: every query face passes exactly
+    through lattice points, the hit count is the product of the closed index ranges -- on the
+    quantised image and on the float blocks"""
+    side = 24 if dim == 3 else 90
+    axes = np.meshgrid(*[np.arange(side)] * dim, indexing="ij")
+    pts = np.stack([a.ravel() for a in axes], axis=1).astype(np.float32) * np.float32(0.125)
+    rng = np.random.default_rng(77)
+    lo = rng.integers(-2, side, (4000, dim))
+    hi = lo + rng.integers(0, 7, (4000, dim))
+    q = np.stack([lo, hi], axis=1).astype(np.float32) * np.float32(0.125)
+    want_counts = np.prod(np.clip(np.minimum(hi, side - 1) - np.maximum(lo, 0) + 1, 0, None), axis=1)
+    with rtb.RTree(kind).insert(pts).flatten_device().upload(0) as tree:
+        for quantised in (1, 0):
+            tree.set_option(rtb.RT_OPT_QUANTISED, quantised)
+            off, ids = tree.query_boxes(q)
+            assert np.array_equal(np.diff(off.astype(np.int64)), want_counts)
+            k = int(np.argmax(want_counts))
+            got = pts[ids[off[k]:off[k + 1]]]
+            assert np.all(got >= q[k, 0]) and np.all(got <= q[k, 1])
