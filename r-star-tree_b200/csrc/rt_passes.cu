@@ -11,6 +11,19 @@
 namespace rtb
 {
 
+// SMs of the current device (148 on a B200); grids of the grid-stride passes are multiples of it
+static unsigned sm_count()
+{
+  int device = 0, sms = 0;
+  if (cudaGetDevice(&device) != cudaSuccess
+      || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0)
+  {
+    cudaGetLastError();
+    return 148u;
+  }
+  return (unsigned)sms;
+}
+
 // ================================ work distribution =================================
 cudaError_t plan_work(const void* kernel, size_t smem, uint64_t n, int forced_grid, cudaStream_t stream,
                       WorkRanges& work, int& grid)
@@ -332,7 +345,8 @@ cudaError_t launch_sort_segments(const uint32_t* big_list, const uint32_t* big_c
 {
   if (max_segments == 0)
     return cudaSuccess;
-  const unsigned grid = max_segments < 148u * 4u ? max_segments : 148u * 4u;
+  const unsigned wave = sm_count() * 4u;
+  const unsigned grid = max_segments < wave ? max_segments : wave;
   sort_segments_kernel<<<grid, SORT_THREADS, 0, stream>>>(big_list, big_count_dev, offsets, ids);
   *launches += 1;
   return cudaGetLastError();
@@ -505,7 +519,7 @@ cudaError_t launch_reorder(const void* queries, uint32_t scalar, uint32_t dim, u
   base += align256(scan_scratch_bytes(CELL_COUNT + 1));
   uint32_t* cell_of_query = reinterpret_cast<uint32_t*>(base);
 
-  const unsigned grid = 148 * 8;
+  const unsigned grid = sm_count() * 8u;
   reorder_init<<<grid, 256, 0, stream>>>(rs, cell_count);
   *launches += 1;
   switch (scalar)
