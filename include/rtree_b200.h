@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1u
+#define RT_ABI_VERSION 2u
 
 /* error codes */
 #define RT_OK 0
@@ -75,13 +75,19 @@ extern "C" {
 #define RT_RESULT_ON_DEVICE 0x2u  /* leave the result in device memory (no D2H copy)      */
 #define RT_UNSORTED 0x4u          /* per-query ids in traversal order (still deterministic)*/
 #define RT_COUNT_ONLY 0x8u        /* fill offsets / total only, no ids                    */
-#define RT_COLLECT_VISITS 0x10u   /* also count node visits (rt_stats), slower            */
+#define RT_COLLECT_VISITS 0x10u   /* also count node visits (rt_stats), slower; counted on the
+                                     image the call traverses (see RT_OPT_QUANTISED)         */
 #define RT_NO_REORDER 0x20u       /* process queries in input order (no coherence pass)   */
 #define RT_ANY_HIT 0x40u          /* rt_query_boxes: stop each query at its first hit -- the
                                      functor-returns-true abort of reference rtree.hpp:994-997.
                                      Implies RT_COUNT_ONLY; offsets[q+1] - offsets[q] is 0 or 1
                                      ("does the box hit anything"; which hit came first depends
                                      on the traversal order and is not reported)            */
+
+#define RT_RESULT_COUNTS32 0x80u   /* rt_query_boxes with a HOST result: deliver rt_hits.counts (32-bit hits per
+                                     query) instead of rt_hits.offsets (64-bit prefix sums, which the ids make
+                                     redundant): 4 instead of 8 bytes per query cross PCIe.  rt_hits.offsets
+                                     is then NULL; ids are laid out exactly as without the flag            */
 
 /* An id slot that holds no entry.  Ids / value counts must stay below it.            */
 #define RT_INVALID_ID 0xFFFFFFFFu
@@ -158,10 +164,12 @@ typedef struct rt_hits
 {
   uint64_t n_queries;
   uint64_t total;
-  const uint64_t* offsets; /* [n_queries + 1] */
+  const uint64_t* offsets; /* [n_queries + 1]; NULL with RT_RESULT_COUNTS32 */
   const uint32_t* ids;     /* [total]; NULL with RT_COUNT_ONLY */
   uint32_t memory;         /* RT_MEM_HOST (pinned) | RT_MEM_DEVICE */
   uint32_t reserved;
+  const uint32_t* counts;  /* [n_queries] hits per query: with RT_RESULT_COUNTS32, and always for a
+                              single-batch device result; else NULL */
 } rt_hits;
 
 typedef struct rt_ray_result
@@ -196,6 +204,8 @@ typedef struct rt_stats
   uint64_t traverse_steps;    /* warp loop iterations; visits / (steps * 32/W) = lane-group use */
   uint32_t batches;           /* batches the call was cut into (> 1: pipelined, see RT_OPT_PIPELINE_BATCH) */
   uint32_t reserved;
+  uint64_t leaf_lookups;      /* RT_COLLECT_VISITS on a quantised image: leaf candidates that had to be looked
+                                 up on the float records (those in a boundary cell of their query) */
 } rt_stats;
 
 /* Copy the tree image to `device` (cudaSetDevice(device) is called by every entry
@@ -268,7 +278,8 @@ int rt_get_stats(const rt_tree* tree, rt_stats* out);
 /* RT_OPT_QUANTISED: 1 (default) = box queries on 3-D float32 point-keyed trees with 8-wide blocks
  *   traverse the quantised image rt_upload builds for them (16-byte slot records with conservative
  *   15-bit bounds; leaf candidates are confirmed on the float records, so results are identical);
- *   0 = always the float blocks.  RT_COLLECT_VISITS always uses the float blocks.            */
+ *   0 = always the float blocks (the reference's exact filter: what SURVEY.md 8d's visit counts
+ *   are defined on).                                                                           */
 #define RT_OPT_QUANTISED 5u
 int rt_set_option(rt_tree* tree, uint32_t option, uint64_t value);
 /* Device copy of the blocks, e.g. to broadcast the tree to peer GPUs.               */

@@ -10,10 +10,11 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librtree_b200.so")
+# RTB_LIB names another build of the same library (the experiment variants of csrc/Makefile)
+LIB_PATH = os.environ.get("RTB_LIB") or os.path.join(_HERE, "csrc", "librtree_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "rtree_b200.h")
 
-RT_ABI_VERSION = 1
+RT_ABI_VERSION = 2
 RT_OK, RT_E_INVALID, RT_E_UNSUPPORTED, RT_E_CUDA, RT_E_NOMEM, RT_E_INTERNAL = 0, -1, -2, -3, -4, -5
 RT_F32, RT_F64, RT_I32 = 0, 1, 2
 RT_KEY_POINT, RT_KEY_BOX = 0, 1
@@ -22,6 +23,7 @@ RT_POINT_IN_BOX, RT_INTERSECTS, RT_CONTAINS = 0, 1, 2
 RT_RAY_ALL_HITS, RT_RAY_CLOSEST, RT_RAY_ANY = 0, 1, 2
 RT_QUERIES_ON_DEVICE, RT_RESULT_ON_DEVICE, RT_UNSORTED = 0x1, 0x2, 0x4
 RT_COUNT_ONLY, RT_COLLECT_VISITS, RT_NO_REORDER, RT_ANY_HIT = 0x8, 0x10, 0x20, 0x40
+RT_RESULT_COUNTS32 = 0x80
 RT_INVALID_ID = 0xFFFFFFFF
 RT_OPT_PIPELINE_BATCH, RT_OPT_QUERY_CHUNK, RT_OPT_WORK_RANGES, RT_OPT_TRAVERSE_GRID = 1, 2, 3, 4
 RT_OPT_QUANTISED = 5
@@ -53,7 +55,8 @@ class RtTreeDesc(C.Structure):
 
 class RtHits(C.Structure):
     _fields_ = [("n_queries", C.c_uint64), ("total", C.c_uint64), ("offsets", C.c_void_p),
-                ("ids", C.c_void_p), ("memory", C.c_uint32), ("reserved", C.c_uint32)]
+                ("ids", C.c_void_p), ("memory", C.c_uint32), ("reserved", C.c_uint32),
+                ("counts", C.c_void_p)]
 
 
 class RtRayResult(C.Structure):
@@ -73,7 +76,7 @@ class RtStats(C.Structure):
                 ("kernel_launches", C.c_uint32), ("deferred_queries", C.c_uint32),
                 ("visits_internal", C.c_uint64), ("visits_leaf", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("traverse_steps", C.c_uint64),
-                ("batches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("batches", C.c_uint32), ("reserved", C.c_uint32), ("leaf_lookups", C.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -206,12 +209,15 @@ class DeviceTree:
         return out
 
     def query_boxes(self, boxes, mode=RT_POINT_IN_BOX, flags=0):
-        """boxes: host array [n][2][dim] -> (offsets[n+1] uint64, ids uint32) numpy copies."""
+        """boxes: host array [n][2][dim] -> (offsets[n+1] uint64, ids uint32) numpy copies
+        (with RT_RESULT_COUNTS32: (counts[n] uint32, ids))."""
         q = np.ascontiguousarray(boxes, self.dtype).reshape(-1, 2, self.dim)
         flags &= ~(RT_QUERIES_ON_DEVICE | RT_RESULT_ON_DEVICE)
         out = self.query_boxes_raw(q.ctypes.data, len(q), mode, flags)
-        offsets = _host_array(out.offsets, out.n_queries + 1, np.uint64)
         ids = _host_array(out.ids, 0 if flags & (RT_COUNT_ONLY | RT_ANY_HIT) else out.total, np.uint32)
+        if flags & RT_RESULT_COUNTS32:  # 32-bit hits per query instead of the 64-bit offsets
+            return _host_array(out.counts, out.n_queries, np.uint32), ids
+        offsets = _host_array(out.offsets, out.n_queries + 1, np.uint64)
         return offsets, ids
 
     def refit(self, keys):

@@ -31,6 +31,7 @@ struct TreeDev
   uint32_t qleaf_link_begin;
   uint32_t qnull_link;
   float qlo[8], qscale[8];          // the grid: q(v) = clamp(floor((v - qlo) * qscale) + 1, 1, 32767)
+  uint32_t stage_links;             // links below this name the nodes of levels 0..2 (RTB_STAGE_TOP experiment)
   uint32_t num_nodes;
   uint32_t num_levels;
 };
@@ -79,7 +80,14 @@ struct BoxLaunch
 {
   TreeDev tree;
   const void* queries;      // [n][2][dim] scalars (device)
-  const uint32_t* order;    // nullable: i-th processed query is order[i]
+  // Quantised trees of dim <= 3 ("packed" launches): the queries as the coherence pass (or
+  // launch_pack_queries) left them -- in processing order, already on the tree's grid, 16 bytes each:
+  // { b_0 .. b_{dim-1}, original index } (dim 2: one unused word).  A query is then one 128-bit load and
+  // the float box is only looked at when a leaf candidate sits in a boundary cell of the query.
+  const uint4* packed;
+  // nullable: i-th processed query is order[i] -- an original query index, or for packed launches a
+  // position in `packed` (only the deferred second pass of a packed launch has one)
+  const uint32_t* order;
   uint64_t n;               // number of queries to process (length of order if given)
   uint32_t pass;
   // outputs / inputs by pass
@@ -96,7 +104,8 @@ struct BoxLaunch
   uint32_t* big_list;               // queries whose list must be sorted afterwards (STASH spills, WRITE)
   uint32_t* big_count;
   WorkRanges work;                  // cursors = MAX_WORK_RANGES entries; the rest is set by the launcher
-  unsigned long long* visit_stats;  // [2] internal / leaf visits (COUNT_STATS)
+  unsigned long long* visit_stats;  // [0] internal / [1] leaf visits, [3] loop steps (COUNT_STATS)
+  unsigned long long* confirm_stats; // [0] leaf candidates looked up on the float records (COUNT_STATS)
   uint32_t sorted;                  // 0: keep traversal order
   uint32_t stop_at_first;           // PASS_COUNT: abort a query at its first hit (RT_ANY_HIT): counts are 0 / 1
   int grid;                         // 0: fill the GPU; > 0: exactly; < 0: fill, less -grid CTAs per SM
@@ -121,7 +130,8 @@ struct RayLaunch
   const uint32_t* order;
   uint64_t n;
   uint32_t mode;         // RT_RAY_*
-  uint32_t pass;         // PASS_COUNT / PASS_COUNT_STATS / PASS_WRITE for ALL_HITS; ignored otherwise
+  uint32_t pass;         // ALL_HITS: PASS_COUNT / PASS_COUNT_STATS / PASS_WRITE; closest / any: PASS_COUNT_STATS
+                         // also counts the node visits, anything else does not
   uint32_t* counts;
   const unsigned long long* offsets;
   uint32_t* ids;
@@ -197,8 +207,14 @@ cudaError_t launch_sort_segments(const uint32_t* big_list, const uint32_t* big_c
 size_t reorder_scratch_bytes(uint64_t n);
 // hi_offset: where the second corner of a query starts (dim for boxes; 0 for points, whose centre is
 // the point itself)
+// packed != nullptr (float32 boxes, dim 2 or 3): instead of order[], write the queries themselves in
+// processing order, quantised on `tree`'s grid (BoxLaunch::packed)
 cudaError_t launch_reorder(const void* queries, uint32_t scalar, uint32_t dim, uint32_t floats_per_query,
                            uint64_t n, uint32_t* order, void* scratch, cudaStream_t stream,
-                           uint32_t* launches, uint32_t hi_offset = 0xFFFFFFFFu);
+                           uint32_t* launches, uint32_t hi_offset = 0xFFFFFFFFu, uint4* packed = nullptr,
+                           const TreeDev* tree = nullptr);
+// packed[i] = query i on the tree's grid, in input order (RT_NO_REORDER and small batches)
+cudaError_t launch_pack_queries(const void* queries, uint32_t dim, uint64_t n, uint4* packed, const TreeDev& tree,
+                                cudaStream_t stream, uint32_t* launches);
 
 } // namespace rtb

@@ -1,4 +1,5 @@
-// rt_knn.cu -- instantiations and launcher of the kNN traversal kernel (float32, 2-D / 3-D, W = 8).
+// rt_knn.cu -- instantiations and launcher of the kNN traversal kernel: every float32 (dim, width) pair
+// the box kernels are instantiated for (rt_box_f32.cu), point and box keys.
 #include "rt_traverse_knn.cuh"
 
 namespace rtb
@@ -24,22 +25,35 @@ cudaError_t launch_knn_kind(const KnnLaunch& p)
   kernel<<<grid, TRAVERSE_THREADS, smem, p.stream>>>(q);
   return cudaGetLastError();
 }
+
+typedef cudaError_t (*knn_launch_fn)(const KnnLaunch&);
+
+#define RTB_KNN_CASE(D, W)                                                                     \
+  if (dim == D && width == W)                                                                  \
+    return box ? &launch_knn_kind<D, W, true> : &launch_knn_kind<D, W, false>;
+
+knn_launch_fn find_knn_kernel(uint32_t dim, uint32_t width, bool box)
+{
+  RTB_KNN_CASE(1, 8)
+  RTB_KNN_CASE(2, 8)
+  RTB_KNN_CASE(3, 8)
+  RTB_KNN_CASE(4, 8)
+  RTB_KNN_CASE(8, 8)
+  RTB_KNN_CASE(2, 16)
+  RTB_KNN_CASE(3, 16)
+  RTB_KNN_CASE(8, 16)
+  return nullptr;
+}
 } // namespace
 
 bool knn_supported(uint32_t scalar, uint32_t dim, uint32_t width)
 {
-  return scalar == RT_F32 && (dim == 2 || dim == 3) && width == 8;
+  return scalar == RT_F32 && find_knn_kernel(dim, width, false) != nullptr;
 }
 
 cudaError_t launch_knn_kernel(const KnnLaunch& p, uint32_t dim, uint32_t width, uint32_t key_kind)
 {
-  if (width != 8)
-    return cudaErrorInvalidValue;
-  const bool box = key_kind == RT_KEY_BOX;
-  if (dim == 2)
-    return box ? launch_knn_kind<2, 8, true>(p) : launch_knn_kind<2, 8, false>(p);
-  if (dim == 3)
-    return box ? launch_knn_kind<3, 8, true>(p) : launch_knn_kind<3, 8, false>(p);
-  return cudaErrorInvalidValue;
+  const knn_launch_fn launch = find_knn_kernel(dim, width, key_kind == RT_KEY_BOX);
+  return launch ? launch(p) : cudaErrorInvalidValue;
 }
 } // namespace rtb

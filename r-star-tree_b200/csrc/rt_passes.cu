@@ -5,6 +5,7 @@
 //   * query reordering by Morton cell (coherence pass)
 // All are bandwidth-trivial next to the traversal (a few bytes per query).
 #include "rt_common.cuh"
+#include "rt_quant.cuh"
 
 #include <cstdlib>
 
@@ -483,6 +484,63 @@ __global__ void __launch_bounds__(256) reorder_scatter(const uint32_t* __restric
   }
 }
 
+// the quantisation grid of a tree, by value
+struct PackGrid
+{
+  float lo[3], scale[3];
+};
+
+// query i of the caller's array as a packed record: its box on the tree's grid + its index
+template <int D>
+__device__ __forceinline__ uint4 pack_query(const float* __restrict__ q, uint64_t i, const PackGrid& g)
+{
+  float lo[D], hi[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+  {
+    lo[d] = q[i * (2 * D) + d];
+    hi[d] = q[i * (2 * D) + D + d];
+  }
+  uint32_t b[D];
+  quant_query<D>(lo, hi, g.lo, g.scale, b);
+  return D == 3 ? make_uint4(b[0], b[1], b[2], (uint32_t)i) : make_uint4(b[0], b[1], (uint32_t)i, 0u);
+}
+
+// the scatter of the coherence pass for packed launches: the query itself, quantised, goes to its
+// place in the processing order (BoxLaunch::packed)
+template <int D>
+__global__ void __launch_bounds__(256) reorder_scatter_packed(const float* __restrict__ q,
+                                                              const uint32_t* __restrict__ cell_of_query, uint64_t n,
+                                                              const unsigned long long* __restrict__ cell_begin,
+                                                              uint32_t* cell_fill, uint4* packed, PackGrid g)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const uint32_t c = cell_of_query[i];
+    const uint32_t k = atomicAdd(&cell_fill[c], 1u);
+    packed[cell_begin[c] + k] = pack_query<D>(q, i, g);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) pack_queries_kernel(const float* __restrict__ q, uint64_t n, uint4* packed,
+                                                           PackGrid g)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    packed[i] = pack_query<D>(q, i, g);
+}
+
+static PackGrid pack_grid(const TreeDev& tree)
+{
+  PackGrid g;
+  for (int d = 0; d < 3; ++d)
+  {
+    g.lo[d] = tree.qlo[d];
+    g.scale[d] = tree.qscale[d];
+  }
+  return g;
+}
+
 __global__ void zero_u32(uint32_t* p, uint32_t n)
 {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -501,12 +559,33 @@ size_t reorder_scratch_bytes(uint64_t n)
          + align256(n * sizeof(uint32_t));
 }
 
-cudaError_t launch_reorder(const void* queries, uint32_t scalar, uint32_t dim, uint32_t scalars_per_query,
-                           uint64_t n, uint32_t* order, void* scratch, cudaStream_t stream,
-                           uint32_t* launches, uint32_t hi_offset)
+cudaError_t launch_pack_queries(const void* queries, uint32_t dim, uint64_t n, uint4* packed, const TreeDev& tree,
+                                cudaStream_t stream, uint32_t* launches)
 {
   if (n == 0)
     return cudaSuccess;
+  const uint64_t want = (n + 255) / 256;
+  const unsigned cap = sm_count() * 8u;
+  const unsigned grid = want < cap ? (unsigned)want : cap;
+  const float* q = static_cast<const float*>(queries);
+  if (dim == 3)
+    pack_queries_kernel<3><<<grid, 256, 0, stream>>>(q, n, packed, pack_grid(tree));
+  else if (dim == 2)
+    pack_queries_kernel<2><<<grid, 256, 0, stream>>>(q, n, packed, pack_grid(tree));
+  else
+    return cudaErrorInvalidValue;
+  *launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reorder(const void* queries, uint32_t scalar, uint32_t dim, uint32_t scalars_per_query,
+                           uint64_t n, uint32_t* order, void* scratch, cudaStream_t stream,
+                           uint32_t* launches, uint32_t hi_offset, uint4* packed, const TreeDev* tree)
+{
+  if (n == 0)
+    return cudaSuccess;
+  if (packed != nullptr && (tree == nullptr || scalar != RT_F32 || (dim != 2 && dim != 3) || scalars_per_query != 2 * dim))
+    return cudaErrorInvalidValue;
   const uint32_t hi = hi_offset == 0xFFFFFFFFu ? dim : hi_offset;
   unsigned char* base = static_cast<unsigned char*>(scratch);
   ReorderScratch* rs = reinterpret_cast<ReorderScratch*>(base);
@@ -546,7 +625,14 @@ cudaError_t launch_reorder(const void* queries, uint32_t scalar, uint32_t dim, u
   if (err != cudaSuccess)
     return err;
   zero_u32<<<grid, 256, 0, stream>>>(cell_count, CELL_COUNT + 1);
-  reorder_scatter<<<grid, 256, 0, stream>>>(cell_of_query, n, cell_begin, cell_count, order);
+  if (packed == nullptr)
+    reorder_scatter<<<grid, 256, 0, stream>>>(cell_of_query, n, cell_begin, cell_count, order);
+  else if (dim == 3)
+    reorder_scatter_packed<3><<<grid, 256, 0, stream>>>(static_cast<const float*>(queries), cell_of_query, n, cell_begin,
+                                                        cell_count, packed, pack_grid(*tree));
+  else
+    reorder_scatter_packed<2><<<grid, 256, 0, stream>>>(static_cast<const float*>(queries), cell_of_query, n, cell_begin,
+                                                        cell_count, packed, pack_grid(*tree));
   *launches += 2;
   return cudaGetLastError();
 }

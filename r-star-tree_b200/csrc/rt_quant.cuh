@@ -64,7 +64,9 @@ __device__ __forceinline__ void quant_slot(const float (&lo)[D], const float (&h
 #pragma unroll
   for (int d = 0; d < D; ++d)
   {
-    h[d] = quant(hi[d], glo[d], gscale[d]);
+    // a NaN bound must not constrain (the reference's comparisons are all false on NaN): an upper
+    // bound goes to the top of the grid, a lower bound to the bottom
+    h[d] = quant_upper(hi[d], glo[d], gscale[d]);
     h[D + d] = 32768u - quant(lo[d], glo[d], gscale[d]);
   }
   quant_pack<D>(h, QUANT_GUARD, a);
@@ -85,13 +87,34 @@ __device__ __forceinline__ void quant_query(const float (&qlo)[D], const float (
   quant_pack<D>(h, 0u, b);
 }
 
+// the guard bits that survive: all of them (== QUANT_GUARD) iff the slot passes
 template <int D>
-__device__ __forceinline__ bool quant_pass(const uint32_t* a, const uint32_t (&b)[D])
+__device__ __forceinline__ uint32_t quant_pass_bits(const uint32_t* a, const uint32_t (&b)[D])
 {
   uint32_t t = a[0] - b[0];
 #pragma unroll
   for (int j = 1; j < D; ++j)
     t &= a[j] - b[j];
+  return t & QUANT_GUARD;
+}
+template <int D>
+__device__ __forceinline__ bool quant_pass(const uint32_t* a, const uint32_t (&b)[D])
+{
+  return quant_pass_bits<D>(a, b) == QUANT_GUARD;
+}
+
+// Strictly inside on the grid: every half-word of a exceeds its half-word of b (a >= b + 1).  For a
+// leaf slot (a from the point p, b from the query box) this means q(p) > q(qlo) and q(p) < q(qhi) on
+// every axis, and because q is monotone non-decreasing that implies qlo < p < qhi: the exact test of
+// the reference (include/RTree/aabb.hpp:206-210) is known to pass without looking at the floats.
+// Only candidates in a boundary cell of the query (about 2 % of them) need the float record.
+template <int D>
+__device__ __forceinline__ bool quant_strictly_inside(const uint32_t* a, const uint32_t (&b)[D])
+{
+  uint32_t t = a[0] - b[0] - 0x00010001u;
+#pragma unroll
+  for (int j = 1; j < D; ++j)
+    t &= a[j] - b[j] - 0x00010001u;
   return (t & QUANT_GUARD) == QUANT_GUARD;
 }
 

@@ -38,8 +38,12 @@ cudaError_t launch_ray_layout(const RayLaunch& p)
     case PASS_WRITE: return launch_ray_mode<W, BOXKEY, RAY_WRITE>(p);
     default: return cudaErrorInvalidValue;
     }
-  case RT_RAY_CLOSEST: return launch_ray_mode<W, BOXKEY, RAY_CLOSEST>(p);
-  case RT_RAY_ANY: return launch_ray_mode<W, BOXKEY, RAY_ANY>(p);
+  case RT_RAY_CLOSEST:
+    return p.pass == PASS_COUNT_STATS ? launch_ray_mode<W, BOXKEY, RAY_CLOSEST_STATS>(p)
+                                      : launch_ray_mode<W, BOXKEY, RAY_CLOSEST>(p);
+  case RT_RAY_ANY:
+    return p.pass == PASS_COUNT_STATS ? launch_ray_mode<W, BOXKEY, RAY_ANY_STATS>(p)
+                                      : launch_ray_mode<W, BOXKEY, RAY_ANY>(p);
   default: return cudaErrorInvalidValue;
   }
 }

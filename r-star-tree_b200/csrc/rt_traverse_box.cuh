@@ -64,14 +64,49 @@ __device__ __forceinline__ void claim_stash_slab(const BoxLaunch& p, int lane, u
 }
 
 // QUANT: traverse the quantised image (rt_quant.cuh) -- one 16-byte record per slot, one integer
-// test for internal children and leaf points alike, leaf candidates confirmed on the float record.
+// test for internal children and leaf points alike.  A leaf candidate strictly inside the query on the
+// grid is a hit as it stands; only candidates in a boundary cell of the query (about 2 %) are looked up
+// on the float record and tested with the reference's comparisons.
+// PACKED (QUANT, dim <= 3): the queries arrive in processing order, already quantised, 16 bytes each
+// (BoxLaunch::packed) -- one 128-bit load per query instead of an index, six floats and six
+// quantisations per warp.
+//
+// __syncwarp() inside the traversal loop.  The stack is written and read by different lanes, so the
+// loop needs the lanes to stay together.  They do: every step has full-mask ballots between the pop
+// and the push, and from the last ballot to the next pop there is no divergent branch (the push is
+// predicated, the leaf branch is decided by a ballot result).  RTB_LOOP_SYNCWARP = 1 keeps the explicit
+// barriers (two issue slots per step); 0 relies on the ballots.
+#ifndef RTB_LOOP_SYNCWARP
+#define RTB_LOOP_SYNCWARP 1
+#endif
+#if RTB_LOOP_SYNCWARP
+#define RTB_LOOP_SYNC() __syncwarp()
+#else
+#define RTB_LOOP_SYNC() ((void)0)
+#endif
+// RTB_STAGE_TOP = 1 (experiment, north_star's "top levels staged in shared memory"): every CTA copies
+// the quantised blocks of the top levels (TreeDev::stage_links) into shared memory and reads them
+// from there.  Measured and left off.
+#ifndef RTB_STAGE_TOP
+#define RTB_STAGE_TOP 0
+#endif
+// RTB_PROGRESSIVE_ROWS (experiments on the 8-D kernel, whose quantised records are two 16-byte rows and a
+// link row): 0 = every lane loads the whole record; 1 = row by row, a lane stops fetching once its slot
+// has failed (measured: 16 % SLOWER -- the rows' L2 latencies add up on the step's dependent chain and
+// the skipped sectors do not make up for it); 2 = both rows at once, the link row only for slots that
+// passed.  DESIGN.md section 8 has the numbers.
+#ifndef RTB_PROGRESSIVE_ROWS
+#define RTB_PROGRESSIVE_ROWS 0
+#endif
+
 template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS, bool QUANT = false>
-__global__ void __launch_bounds__(TRAVERSE_THREADS)
+__global__ void __launch_bounds__(TRAVERSE_THREADS, QUANT ? 8 : 1) // quantised kernels: 32 registers, 64 warps per SM
 box_traverse_kernel(const BoxLaunch p)
 {
-  static_assert(!QUANT || (std::is_same<S, float>::value && !BOXKEY && PASS != PASS_COUNT_STATS),
+  static_assert(!QUANT || (std::is_same<S, float>::value && !BOXKEY),
                 "the quantised image exists for float32 point-keyed trees");
   constexpr int G = 32 / W;
+  constexpr bool PACKED = QUANT && D <= 3;
   extern __shared__ uint32_t smem[];
 
   const int lane = threadIdx.x & 31;
@@ -94,6 +129,22 @@ box_traverse_kernel(const BoxLaunch p)
   if (lane < G)
     sts_u32(stack - G * 4u + lane * 4u, null_link);
   __syncwarp();
+#if RTB_STAGE_TOP
+  // the top of the quantised image, once per CTA, behind the warps' stacks
+  const uint32_t stage_links = QUANT ? p.tree.stage_links : 0u;
+  const uint32_t stage_base = smem_addr(smem + (TRAVERSE_THREADS / 32) * (HIT_BUF + G + stack_cap)) + slot * 16u;
+  if constexpr (QUANT)
+  {
+    for (uint32_t k = threadIdx.x; k < stage_links; k += TRAVERSE_THREADS)
+    {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.tree.qblocks) + k);
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage_base - slot * 16u + k * 16u), "r"(v.x),
+                   "r"(v.y), "r"(v.z), "r"(v.w)
+                   : "memory");
+    }
+    __syncthreads();
+  }
+#endif
 
   // this lane's element of a row
   const unsigned char* lane_blocks = opaque((QUANT ? p.tree.qblocks : p.tree.blocks) + slot * 16);
@@ -102,7 +153,7 @@ box_traverse_kernel(const BoxLaunch p)
   const uint32_t leaf_link_begin = QUANT ? p.tree.qleaf_link_begin : p.tree.leaf_link_begin;
   const S* __restrict__ queries = static_cast<const S*>(p.queries);
 
-  unsigned long long visits_int = 0, visits_leaf = 0, steps = 0;
+  unsigned long long visits_int = 0, visits_leaf = 0, steps = 0, lookups = 0;
   // stash slab owned by this warp (PASS_STASH)
   unsigned long long slab_pos = 0;
   uint32_t slab_left = 0;
@@ -128,18 +179,33 @@ box_traverse_kernel(const BoxLaunch p)
     // stack pointer and ballots out of the uniform datapath, which costs 20 % -- measured)
     for (unsigned long long i = begin; i < last; ++i)
     {
-      const unsigned long long qi = p.order ? (unsigned long long)p.order[i] : i;
+      unsigned long long qi;  // the query's index in the caller's array
+      uint32_t defer_key;     // what the deferred list holds for it: see BoxLaunch::order
       S qlo[D], qhi[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d)
-      {
-        qlo[d] = __ldg(queries + qi * (2 * D) + d);
-        qhi[d] = __ldg(queries + qi * (2 * D) + D + d);
-      }
-
       uint32_t qb[D]; // the query on the quantisation grid (QUANT)
-      if constexpr (QUANT)
-        quant_query<D>(qlo, qhi, p.tree.qlo, p.tree.qscale, qb);
+      if constexpr (PACKED)
+      {
+        const unsigned long long pos = p.order ? (unsigned long long)p.order[i] : i;
+        const uint4 v = __ldg(p.packed + pos);
+        qb[0] = v.x, qb[1] = v.y;
+        if constexpr (D == 3)
+          qb[2] = v.z;
+        qi = D == 3 ? v.w : v.z;
+        defer_key = (uint32_t)pos;
+      }
+      else
+      {
+        qi = p.order ? (unsigned long long)p.order[i] : i;
+        defer_key = (uint32_t)qi;
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+        {
+          qlo[d] = __ldg(queries + qi * (2 * D) + d);
+          qhi[d] = __ldg(queries + qi * (2 * D) + D + d);
+        }
+        if constexpr (QUANT)
+          quant_query<D>(qlo, qhi, p.tree.qlo, p.tree.qscale, qb);
+      }
 
       unsigned long long out_base = 0;
       uint32_t expect = 0;
@@ -165,18 +231,75 @@ box_traverse_kernel(const BoxLaunch p)
       {
         const uint32_t node = lds_u32(stack_pop + sp4);
         sp4 -= min(sp4, (uint32_t)(G * 4));
-        __syncwarp();
+        RTB_LOOP_SYNC();
 
         const bool is_leaf = node >= leaf_link_begin;
         uint32_t link;
         bool hit;
+        uint32_t hit_bits = 0; // QUANT: the guard bits that survived; all of them = the slot passes
+        using QRec = Record<D + 1, W>;
+        uint32_t w[QRec::PADDED]; // the slot's quantised record (QUANT)
         if constexpr (QUANT)
         {
-          using Rec = Record<D + 1, W>;
-          uint32_t w[Rec::PADDED];
-          Rec::load(lane_blocks + (unsigned long long)node * 16u, slot, w);
-          link = w[D];
-          hit = quant_pass<D>(w, qb); // empty slots never pass
+          if constexpr (QRec::NV >= 2 && RTB_PROGRESSIVE_ROWS == 2)
+          {
+            // wide records: every row at once, but the link row (a ninth wavefront per step) only for
+            // the slots that passed -- one in sixteen
+            const unsigned char* rec = lane_blocks + (unsigned long long)node * 16u;
+#pragma unroll
+            for (int k = 0; k < QRec::NV; ++k)
+            {
+              const uint4 v = __ldg(reinterpret_cast<const uint4*>(rec + k * W * 16));
+              w[4 * k + 0] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
+            }
+            hit_bits = quant_pass_bits<D>(w, qb);
+            link = RT_INVALID_ID;
+            if (hit_bits == QUANT_GUARD)
+              link = __ldg(reinterpret_cast<const uint32_t*>(rec + QRec::NV * W * 16 - slot * 12));
+            w[D] = link;
+          }
+          else if constexpr (QRec::NV >= 2 && RTB_PROGRESSIVE_ROWS == 1)
+          {
+            // wide records (8-D: two 16-byte rows + the link): row by row, and a lane whose slot has
+            // already failed fetches no more of it.  Nearly every child of a node is rejected (one in
+            // sixteen passes), mostly by its first row, so the second row and the link row are only
+            // read for the few sectors that hold a surviving slot -- the kernel is bound by the
+            // L2 -> L1 fill of its 576-byte nodes, not by instructions.
+            const unsigned char* rec = lane_blocks + (unsigned long long)node * 16u;
+            hit_bits = QUANT_GUARD;
+#pragma unroll
+            for (int k = 0; k < QRec::NV; ++k)
+            {
+              if (hit_bits == QUANT_GUARD)
+              {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(rec + k * W * 16));
+                w[4 * k + 0] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
+                hit_bits &= (v.x - qb[4 * k + 0]) & (v.y - qb[4 * k + 1]) & (v.z - qb[4 * k + 2]) & (v.w - qb[4 * k + 3]);
+              }
+            }
+            static_assert(QRec::R == 1, "the link is the one-word tail of the record");
+            link = RT_INVALID_ID;
+            if (hit_bits == QUANT_GUARD)
+              link = __ldg(reinterpret_cast<const uint32_t*>(rec + QRec::NV * W * 16 - slot * 12));
+            w[D] = link;
+          }
+          else
+          {
+#if RTB_STAGE_TOP
+            if (D == 3 && node < stage_links)
+            {
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                           : "r"(stage_base + node * 16u)
+                           : "memory");
+            }
+            else
+#endif
+              QRec::load(lane_blocks + (unsigned long long)node * 16u, slot, w);
+            link = w[D];
+            hit_bits = quant_pass_bits<D>(w, qb); // empty slots never pass
+          }
+          hit = hit_bits == QUANT_GUARD;
         }
         else
         {
@@ -202,21 +325,49 @@ box_traverse_kernel(const BoxLaunch p)
           }
         }
 
-        const uint32_t m_all = __ballot_sync(0xFFFFFFFFu, hit);
-        const uint32_t m_leaf = __ballot_sync(0xFFFFFFFFu, hit && is_leaf);
-        const uint32_t m_int = m_all & ~m_leaf;
-
-        if (PASS == PASS_COUNT_STATS)
+        uint32_t m_leaf, m_int;
+        if constexpr (QUANT && PASS != PASS_COUNT_STATS)
         {
-          visits_leaf += __popc(__ballot_sync(0xFFFFFFFFu, is_leaf && slot == 0 && node != null_link));
-          visits_int += __popc(__ballot_sync(0xFFFFFFFFu, !is_leaf && slot == 0));
-          ++steps;
+          // the two ballots and the push, spelled out: three compares for (leaf?, hit && leaf, hit &&
+          // !leaf), two votes, and the children that passed go onto the stack in lane order, which keeps
+          // it sorted by level (left to nvcc this part costs four instructions more per step)
+          asm volatile("{\n\t"
+                       ".reg .pred pl, pleaf, pint;\n\t"
+                       ".reg .b32 t;\n\t"
+                       "setp.ge.u32 pl, %3, %4;\n\t"
+                       "setp.eq.and.b32 pleaf, %5, 0x80008000, pl;\n\t"
+                       "setp.eq.and.b32 pint, %5, 0x80008000, !pl;\n\t"
+                       "vote.sync.ballot.b32 %0, pleaf, 0xffffffff;\n\t"
+                       "vote.sync.ballot.b32 %1, pint, 0xffffffff;\n\t"
+                       "and.b32 t, %1, %6;\n\t"
+                       "popc.b32 t, t;\n\t"
+                       "mad.lo.u32 t, t, 4, %7;\n\t"
+                       "@pint st.shared.u32 [t+%10], %8;\n\t"
+                       "popc.b32 t, %1;\n\t"
+                       "mad.lo.u32 %2, t, 4, %9;\n\t"
+                       "}"
+                       : "=r"(m_leaf), "=r"(m_int), "=r"(sp4)
+                       : "r"(node), "r"(leaf_link_begin), "r"(hit_bits), "r"(lt_mask), "r"(warp_mem + sp4), "r"(link),
+                         "r"(sp4), "n"(HITBUF_BELOW)
+                       : "memory");
         }
+        else
+        {
+          m_leaf = __ballot_sync(0xFFFFFFFFu, hit && is_leaf);
+          m_int = __ballot_sync(0xFFFFFFFFu, hit && !is_leaf);
 
-        // children to descend: compact onto the stack in lane order (keeps it level-sorted)
-        if (hit && !is_leaf)
-          sts_u32(stack + sp4 + __popc(m_int & lt_mask) * 4u, link);
-        sp4 += __popc(m_int) * 4u;
+          if (PASS == PASS_COUNT_STATS)
+          {
+            visits_leaf += __popc(__ballot_sync(0xFFFFFFFFu, is_leaf && slot == 0 && node != null_link));
+            visits_int += __popc(__ballot_sync(0xFFFFFFFFu, !is_leaf && slot == 0));
+            ++steps;
+          }
+
+          // children to descend: compact onto the stack in lane order (keeps it level-sorted)
+          if (hit && !is_leaf)
+            sts_u32(stack + sp4 + __popc(m_int & lt_mask) * 4u, link);
+          sp4 += __popc(m_int) * 4u;
+        }
 
         // leaf entries that satisfy the predicate
         if (m_leaf != 0)
@@ -225,38 +376,47 @@ box_traverse_kernel(const BoxLaunch p)
           bool leaf_hit = hit && is_leaf;
           if constexpr (QUANT)
           {
-            // candidates of the quantised test: the reference's exact test on the float record
-            if (leaf_hit)
+            // a candidate strictly inside the query on the grid is a hit; one in a boundary cell of
+            // the query gets the reference's exact test on its float record
+            bool unsure = false;
+            if constexpr (D <= 3)
             {
-              // the float block of a point leaf has the stride of its quantised block
-              using Key = Record<D + 1, W>;
-              uint32_t kw[Key::PADDED];
-              Key::load(lane_blocks + leaf_delta + (unsigned long long)(node - leaf_link_begin) * 16u, slot, kw);
-              S klo[D];
-#pragma unroll
-              for (int d = 0; d < D; ++d)
-                klo[d] = __uint_as_float(kw[d]);
-              if constexpr (D == 3)
+              unsure = leaf_hit && !quant_strictly_inside<D>(w, qb);
+            }
+            else if (leaf_hit)
+            {
+              // wide records are not kept in registers across the ballots (8 registers = a CTA per SM):
+              // the few lanes with a candidate read theirs again, an L1 hit
+              uint32_t again[QRec::PADDED];
+              QRec::load(lane_blocks + (unsigned long long)node * 16u, slot, again);
+              unsure = !quant_strictly_inside<D>(again, qb);
+            }
+            const uint32_t m_unsure = __ballot_sync(0xFFFFFFFFu, unsure);
+            if (m_unsure != 0)
+            {
+              if (unsure)
               {
-                // (written out: the loop form below costs ptxas 8 more registers in the 3-D kernel)
-                leaf_hit = !(klo[0] < qlo[0]) && !(klo[0] > qhi[0]) && !(klo[1] < qlo[1]) && !(klo[1] > qhi[1])
-                           && !(klo[2] < qlo[2]) && !(klo[2] > qhi[2]);
-              }
-              else
-              {
+                // the float block of a point leaf has the stride of its quantised block
+                uint32_t kw[QRec::PADDED];
+                QRec::load(lane_blocks + leaf_delta + (unsigned long long)(node - leaf_link_begin) * 16u, slot, kw);
                 bool inside = true;
+                unsigned long long at_q = qi * (2 * D);
+                asm volatile("" : "+l"(at_q)); // keep the address of the float box out of the loop's registers
 #pragma unroll
                 for (int d = 0; d < D; ++d)
                 {
-                  // wide queries are re-read (an L1 hit) rather than held in 2 D registers all along
-                  const S lo_d = D > 3 ? __ldg(queries + qi * (2 * D) + d) : qlo[d];
-                  const S hi_d = D > 3 ? __ldg(queries + qi * (2 * D) + D + d) : qhi[d];
-                  inside = inside && !(klo[d] < lo_d) && !(klo[d] > hi_d);
+                  // the float box is not kept in registers: re-read (an L1 hit) in this rare path
+                  const S k_d = __uint_as_float(kw[d]);
+                  const S lo_d = __ldg(queries + at_q + d);
+                  const S hi_d = __ldg(queries + at_q + D + d);
+                  inside = inside && !(k_d < lo_d) && !(k_d > hi_d);
                 }
                 leaf_hit = inside;
               }
+              m_hits = __ballot_sync(0xFFFFFFFFu, leaf_hit);
+              if (PASS == PASS_COUNT_STATS)
+                lookups += __popc(m_unsure);
             }
-            m_hits = __ballot_sync(0xFFFFFFFFu, leaf_hit);
           }
           if (PASS == PASS_STASH || PASS == PASS_WRITE)
           {
@@ -286,8 +446,9 @@ box_traverse_kernel(const BoxLaunch p)
             sp4 = 0;
           }
         }
-        __syncwarp();
+        RTB_LOOP_SYNC();
       }
+      __syncwarp(); // the hit buffer is read across lanes below
 
       // ---- end of query ------------------------------------------------------------
       if (PASS == PASS_COUNT || PASS == PASS_COUNT_STATS)
@@ -332,7 +493,7 @@ box_traverse_kernel(const BoxLaunch p)
           p.counts[qi] = count;
           p.stash_pos[qi] = where;
           if (where == NO_STASH)
-            p.deferred_list[atomicAdd(p.deferred_count, 1u)] = (uint32_t)qi;
+            p.deferred_list[atomicAdd(p.deferred_count, 1u)] = defer_key;
         }
       }
       else // PASS_WRITE
@@ -358,6 +519,8 @@ box_traverse_kernel(const BoxLaunch p)
     atomicAdd(p.visit_stats + 0, visits_int);
     atomicAdd(p.visit_stats + 1, visits_leaf);
     atomicAdd(p.visit_stats + 3, steps);
+    if (QUANT)
+      atomicAdd(p.confirm_stats, lookups);
   }
 }
 
@@ -365,7 +528,7 @@ template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS, b
 cudaError_t launch_box_pass(const BoxLaunch& p)
 {
   // the (dim, width) pairs of quant_supported() in rt_quant.cu
-  constexpr bool CAN_QUANT = std::is_same<S, float>::value && !BOXKEY && PASS != PASS_COUNT_STATS
+  constexpr bool CAN_QUANT = std::is_same<S, float>::value && !BOXKEY
                              && ((D == 2 && W == 8) || (D == 3 && W == 8) || (D == 8 && W == 16));
   if constexpr (CAN_QUANT && !QUANT)
   {
@@ -373,7 +536,11 @@ cudaError_t launch_box_pass(const BoxLaunch& p)
       return launch_box_pass<S, D, W, BOXKEY, CONTAINS, PASS, true>(p);
   }
   auto kernel = box_traverse_kernel<S, D, W, BOXKEY, CONTAINS, PASS, QUANT>;
-  const size_t smem = traverse_smem_bytes(p.tree.num_levels, W);
+  size_t smem = traverse_smem_bytes(p.tree.num_levels, W);
+#if RTB_STAGE_TOP
+  if (QUANT)
+    smem += (size_t)p.tree.stage_links * 16u;
+#endif
   cudaError_t err = cudaSuccess;
   if (smem > 48 * 1024)
   {

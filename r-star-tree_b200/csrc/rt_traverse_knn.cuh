@@ -16,9 +16,13 @@
 //     overtaken since they were pushed are dropped when popped;
 //   * the children of one node are pushed far-ones-first, so the nearest are popped next and the
 //     bound tightens early (children of different nodes keep their order: the stack stays sorted
-//     by level, which is what bounds its depth);
-//   * the k best pairs live one per lane (k <= 32); the worst is found with two warp reductions
-//     and the candidates of a leaf step are offered one at a time.
+//     by level, which is what bounds its depth); "far" = more than 4 x the distance of the node's
+//     nearest child, found with a butterfly over the node's lanes;
+//   * the k best pairs are kept SORTED across the lanes (lane i holds the i-th best, k <= 32): a
+//     candidate that beats the worst is inserted with one shuffle-up of the pairs behind it, the
+//     worst is simply lane k-1's pair, and the result needs no sort at the end.  (Round 1 kept them
+//     unsorted, found the worst with two warp reductions per accepted candidate and sorted 64-bit
+//     pairs over the warp per query: 13 k instructions per query, now about a third.)
 #pragma once
 
 #include "rt_block.cuh"
@@ -36,30 +40,6 @@ __device__ __forceinline__ void sts_u32x2(uint32_t addr, uint32_t a, uint32_t b)
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 
-// ascending bitonic sort of one (hi, lo) 64-bit key per lane
-__device__ __forceinline__ void warp_sort32_pair(uint32_t& hi, uint32_t& lo, int lane)
-{
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1)
-  {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1)
-    {
-      const uint32_t ohi = __shfl_xor_sync(0xFFFFFFFFu, hi, j);
-      const uint32_t olo = __shfl_xor_sync(0xFFFFFFFFu, lo, j);
-      const bool ascending = (lane & k) == 0;
-      const bool lower = (lane & j) == 0;
-      const bool mine_less = hi < ohi || (hi == ohi && lo < olo);
-      const bool other_less = ohi < hi || (ohi == hi && olo < lo);
-      if ((lower == ascending) ? other_less : mine_less) // keep the smaller / the larger of the two
-      {
-        hi = ohi;
-        lo = olo;
-      }
-    }
-  }
-}
-
 template <int D, int W, bool BOXKEY>
 __global__ void __launch_bounds__(TRAVERSE_THREADS)
 knn_traverse_kernel(const KnnLaunch p)
@@ -73,7 +53,7 @@ knn_traverse_kernel(const KnnLaunch p)
   const int slot = lane % W;
   const uint32_t grp = lane / W;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t grp_mask = ((1u << W) - 1u) << (grp * W);
+  const uint32_t grp_mask = (W == 32 ? 0xFFFFFFFFu : ((1u << W) - 1u)) << (grp * W);
 
   // per warp: G null entries, then the stack of (link, dist2 bits) pairs
   const uint32_t stack_cap = 32u * p.tree.num_levels;
@@ -88,7 +68,7 @@ knn_traverse_kernel(const KnnLaunch p)
   const unsigned char* lane_blocks = opaque(p.tree.blocks + slot * 16);
   const uint32_t leaf_link_begin = p.tree.leaf_link_begin;
   const uint32_t k = p.k;
-  const bool holder = (uint32_t)lane < k; // this lane holds one of the k best pairs
+  const int last = (int)k - 1; // the lane that holds the worst of the k best
 
   unsigned long long visits_int = 0, visits_leaf = 0;
 
@@ -104,9 +84,9 @@ knn_traverse_kernel(const KnnLaunch p)
       range = range + 1 == p.work.ranges ? 0 : range + 1;
       continue;
     }
-    const unsigned long long last = min(begin + p.work.chunk, (unsigned long long)p.n);
+    const unsigned long long end = min(begin + p.work.chunk, (unsigned long long)p.n);
 
-    for (unsigned long long i = begin; i < last; ++i)
+    for (unsigned long long i = begin; i < end; ++i)
     {
       const unsigned long long qi = p.order ? (unsigned long long)p.order[i] : i;
       float q[D];
@@ -114,8 +94,9 @@ knn_traverse_kernel(const KnnLaunch p)
       for (int d = 0; d < D; ++d)
         q[d] = __ldg(p.points + qi * D + d);
 
-      uint32_t bd2 = INF_BITS, bid = RT_INVALID_ID;       // this lane's pair (holders only)
-      uint32_t wd = INF_BITS, wi = RT_INVALID_ID, wl = 0; // the worst pair and the lane that holds it
+      // the k best, sorted ascending by (d2 bits, id) across lanes 0 .. k-1 (d2 >= +0: bits order)
+      uint32_t bd = INF_BITS, bi = RT_INVALID_ID;
+      uint32_t wd = INF_BITS, wi = RT_INVALID_ID; // the worst of them = lane k-1's pair
 
       uint32_t sp8 = 8u; // bytes on the stack
       if (lane == 0)
@@ -128,7 +109,7 @@ knn_traverse_kernel(const KnnLaunch p)
         lds_u32x2(stack_pop + sp8, node, node_d2);
         sp8 -= min(sp8, (uint32_t)(G * 8));
         __syncwarp();
-        if (node_d2 > wd) // the bound has moved past this node since it was pushed (d2 >= +0: bits order)
+        if (node_d2 > wd) // the bound has moved past this node since it was pushed
           node = null_link;
 
         const bool is_leaf = node >= leaf_link_begin;
@@ -159,7 +140,10 @@ knn_traverse_kernel(const KnnLaunch p)
         const uint32_t m_push = __ballot_sync(0xFFFFFFFFu, push);
         if (m_push != 0)
         {
-          const uint32_t dmin = __reduce_min_sync(grp_mask, push ? d2b : 0xFFFFFFFFu);
+          uint32_t dmin = push ? d2b : 0xFFFFFFFFu; // nearest pushed child of this lane's node
+#pragma unroll
+          for (int s = 1; s < W; s <<= 1)
+            dmin = min(dmin, __shfl_xor_sync(0xFFFFFFFFu, dmin, s));
           const bool is_far = push && d2 > __fmul_rn(__uint_as_float(dmin), 4.0f);
           const uint32_t m_far = __ballot_sync(0xFFFFFFFFu, is_far);
           const uint32_t below = __popc(m_push & ~grp_mask & lt_mask); // pushes of the lower groups
@@ -170,7 +154,7 @@ knn_traverse_kernel(const KnnLaunch p)
           sp8 += __popc(m_push) * 8u;
         }
 
-        // ---- leaf entries that beat the worst of the k best: offered one at a time -----------------
+        // ---- leaf entries that beat the worst of the k best: inserted one at a time -----------------
         uint32_t m_cand = __ballot_sync(0xFFFFFFFFu, valid && is_leaf && (d2b < wd || (d2b == wd && link < wi)));
         while (m_cand != 0)
         {
@@ -178,28 +162,30 @@ knn_traverse_kernel(const KnnLaunch p)
           m_cand &= m_cand - 1;
           const uint32_t cd = __shfl_sync(0xFFFFFFFFu, d2b, src);
           const uint32_t ci = __shfl_sync(0xFFFFFFFFu, link, src);
-          if (cd < wd || (cd == wd && ci < wi))
+          if (cd < wd || (cd == wd && ci < wi)) // still better than the worst (warp-uniform)
           {
-            if ((uint32_t)lane == wl)
+            // every pair behind the candidate's place moves up one lane, the lane at its place takes it
+            const bool behind = bd > cd || (bd == cd && bi > ci);
+            const uint32_t up_d = __shfl_up_sync(0xFFFFFFFFu, bd, 1);
+            const uint32_t up_i = __shfl_up_sync(0xFFFFFFFFu, bi, 1);
+            const bool prev_behind = lane > 0 && (up_d > cd || (up_d == cd && up_i > ci));
+            if (behind)
             {
-              bd2 = cd;
-              bid = ci;
+              bd = prev_behind ? up_d : cd;
+              bi = prev_behind ? up_i : ci;
             }
-            wd = __reduce_max_sync(0xFFFFFFFFu, holder ? bd2 : 0u);
-            wi = __reduce_max_sync(0xFFFFFFFFu, (holder && bd2 == wd) ? bid : 0u);
-            wl = (uint32_t)__ffs(__ballot_sync(0xFFFFFFFFu, holder && bd2 == wd && bid == wi)) - 1u;
+            wd = __shfl_sync(0xFFFFFFFFu, bd, last);
+            wi = __shfl_sync(0xFFFFFFFFu, bi, last);
           }
         }
         __syncwarp();
       }
 
-      // ---- the k pairs, ascending by (d2, id) ---------------------------------------------------
-      uint32_t sd = holder ? bd2 : 0xFFFFFFFFu, si = holder ? bid : 0xFFFFFFFFu;
-      warp_sort32_pair(sd, si, lane);
-      if (holder)
+      // ---- the k pairs, already ascending by (d2, id) ---------------------------------------------
+      if ((uint32_t)lane < k)
       {
-        p.ids_out[qi * k + lane] = si;
-        p.d2_out[qi * k + lane] = __uint_as_float(sd);
+        p.ids_out[qi * k + lane] = bi;
+        p.d2_out[qi * k + lane] = __uint_as_float(bd);
       }
       __syncwarp();
     }

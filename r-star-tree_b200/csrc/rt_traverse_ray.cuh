@@ -30,13 +30,21 @@ enum : uint32_t
   RAY_COUNT_STATS = 1,
   RAY_WRITE = 2,
   RAY_CLOSEST = 3,
-  RAY_ANY = 4
+  RAY_ANY = 4,
+  RAY_CLOSEST_STATS = 5, // closest-hit / any-hit that also count the nodes they visit (RT_COLLECT_VISITS)
+  RAY_ANY_STATS = 6
 };
 
-template <int W, bool BOXKEY, uint32_t RMODE>
+template <int W, bool BOXKEY, uint32_t KMODE>
 __global__ void __launch_bounds__(TRAVERSE_THREADS)
 ray_traverse_kernel(const RayLaunch p)
 {
+  // the *_STATS modes are their base mode plus the visit counters
+  constexpr uint32_t RMODE = KMODE == RAY_COUNT_STATS     ? RAY_COUNT
+                             : KMODE == RAY_CLOSEST_STATS ? RAY_CLOSEST
+                             : KMODE == RAY_ANY_STATS     ? RAY_ANY
+                                                          : KMODE;
+  constexpr bool STATS = KMODE != RMODE;
   constexpr int G = 32 / W;
   constexpr int D = 3;
   extern __shared__ uint32_t smem[];
@@ -144,7 +152,7 @@ ray_traverse_kernel(const RayLaunch p)
         const uint32_t m_leaf = __ballot_sync(0xFFFFFFFFu, hit && is_leaf);
         const uint32_t m_int = m_all & ~m_leaf;
 
-        if (RMODE == RAY_COUNT_STATS)
+        if (STATS)
         {
           visits_leaf += __popc(__ballot_sync(0xFFFFFFFFu, is_leaf && slot == 0 && node != null_link));
           visits_int += __popc(__ballot_sync(0xFFFFFFFFu, !is_leaf && slot == 0));
@@ -198,7 +206,7 @@ ray_traverse_kernel(const RayLaunch p)
         __syncwarp();
       }
 
-      if (RMODE == RAY_COUNT || RMODE == RAY_COUNT_STATS)
+      if (RMODE == RAY_COUNT)
       {
         if (lane == 0)
           p.counts[qi] = count;
@@ -238,7 +246,7 @@ ray_traverse_kernel(const RayLaunch p)
     }
   }
 
-  if (RMODE == RAY_COUNT_STATS && lane == 0)
+  if (STATS && lane == 0)
   {
     atomicAdd(p.visit_stats + 0, visits_int);
     atomicAdd(p.visit_stats + 1, visits_leaf);

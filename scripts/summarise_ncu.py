@@ -2,7 +2,9 @@
 """Summarise an `ncu --set full` report (read here, on the CPU box) into profiles/.
 
   python scripts/summarise_ncu.py gpurun_out/box_traverse_r1b.ncu-rep profiles/r1_v3_box_traverse \
-      [--traffic]   # also (re)write profiles/traffic.json = DRAM bytes per launch of the first kernel
+      [--traffic [--queries N]]   # also (re)write profiles/traffic.json: what bench.py's roofline takes from
+                                  # the capture, per launch of the first kernel (DRAM bytes, warp instructions,
+                                  # L1 bytes, issue utilisation); N = queries that launch answered
 
 Writes <out>_summary.json (the counters DESIGN.md / bench.py quote, one object per profiled launch)
 and <out>_details.csv (ncu's own details page)."""
@@ -79,9 +81,20 @@ def main():
         f.write(ncu("-i", rep, "--page", "details", "--csv"))
     if "--traffic" in sys.argv and launches:
         path = os.path.join(os.path.dirname(out) or ".", "traffic.json")
+        first = launches[0]
+        queries = int(sys.argv[sys.argv.index("--queries") + 1]) if "--queries" in sys.argv else None
+        instr = first.get("warp_instructions")
+        sectors = first.get("global_load_sectors")
         with open(path, "w") as f:
-            json.dump({"kernel": launches[0]["kernel"], "dram_bytes_per_launch": launches[0].get("dram_bytes"),
-                       "source": os.path.basename(out) + "_summary.json"}, f, indent=1)
+            json.dump({"kernel": first["kernel"], "dram_bytes_per_launch": first.get("dram_bytes"),
+                       "warp_instructions_per_launch": instr,
+                       "queries_per_launch": queries,
+                       "warp_instructions_per_query": (instr / queries) if (instr and queries) else None,
+                       "l1_bytes_per_launch": (sectors * 32.0) if sectors else None,
+                       "issue_active_pct": first.get("issue_active_pct"),
+                       "l1_hit_pct": first.get("l1_hit_pct"), "l2_hit_pct": first.get("l2_hit_pct"),
+                       "kernel_ms_under_ncu": first.get("duration_s", 0.0) * 1e3,
+                       "source": "profiles/" + os.path.basename(out) + "_summary.json"}, f, indent=1)
     for d in launches:
         print(json.dumps(d))
 

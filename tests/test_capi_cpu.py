@@ -32,12 +32,12 @@ def test_every_declared_symbol_is_exported(rtb):
 
 def test_abi_version_and_struct_sizes(rtb):
     capi = rtb.capi
-    assert capi.lib().rt_abi_version() == capi.RT_ABI_VERSION == 1
+    assert capi.lib().rt_abi_version() == capi.RT_ABI_VERSION == 2
     # x86-64 layouts of the structs in include/rtree_b200.h
     assert C.sizeof(capi.RtTreeDesc) == 88
-    assert C.sizeof(capi.RtHits) == 40
-    assert C.sizeof(capi.RtRayResult) == 88
-    assert C.sizeof(capi.RtStats) == 72
+    assert C.sizeof(capi.RtHits) == 48
+    assert C.sizeof(capi.RtRayResult) == 96
+    assert C.sizeof(capi.RtStats) == 80
     assert C.sizeof(capi.RtKnnResult) == 32
 
 
@@ -46,7 +46,7 @@ def test_header_compiles_as_plain_c(rtb, tmp_path):
     src.write_text('#include <rtree_b200.h>\n#include <stddef.h>\n'
                    'int sizes[5] = { sizeof(rt_tree_desc), sizeof(rt_hits), sizeof(rt_ray_result), sizeof(rt_stats),\n'
                    '                 sizeof(rt_knn_result) };\n'
-                   'int main(void) { return sizes[0] == 88 && sizes[1] == 40 && sizes[2] == 88 && sizes[3] == 72\n'
+                   'int main(void) { return sizes[0] == 88 && sizes[1] == 48 && sizes[2] == 96 && sizes[3] == 80\n'
                    '                        && sizes[4] == 32 ? 0 : 1; }\n')
     exe = tmp_path / "abi"
     inc = os.path.dirname(rtb.capi.HEADER_PATH)

@@ -39,12 +39,24 @@ def test_golden_vectors_all_pipelines(rtb, name):
         assert csr_equal(tree.query_boxes(q, mode), want)                                   # stash pipeline
         assert tree.stats()["kernel_launches"] > 0
         assert csr_equal(tree.query_boxes(q, mode, rtb.RT_NO_REORDER), want)
-        off, ids = tree.query_boxes(q, mode, rtb.RT_COLLECT_VISITS)                         # two-pass pipeline
+        # two-pass pipeline with visit counters: on the quantised image (where the tree has one) the
+        # conservative filter may visit a few nodes more than the reference's exact filter ...
+        off, ids = tree.query_boxes(q, mode, rtb.RT_COLLECT_VISITS)
+        assert csr_equal((off, ids), want)
+        sq = tree.stats()
+        _, _, visits = O.oracle_query_boxes(flat, q, mode, want_visits=True)
+        exact = (int(visits[0]), int(visits[1]))
+        assert sq["visits_internal"] >= exact[0] and sq["visits_leaf"] >= exact[1]
+        assert sq["visits_internal"] + sq["visits_leaf"] <= 1.05 * (exact[0] + exact[1]) + 16
+        assert sq["leaf_lookups"] <= 16 * sq["visits_leaf"]
+        # ... and on the float blocks exactly the nodes the reference's traversal visits
+        tree.set_option(rtb.RT_OPT_QUANTISED, 0)
+        off, ids = tree.query_boxes(q, mode, rtb.RT_COLLECT_VISITS)
+        tree.set_option(rtb.RT_OPT_QUANTISED, 1)
         assert csr_equal((off, ids), want)
         s = tree.stats()
-        _, _, visits = O.oracle_query_boxes(flat, q, mode, want_visits=True)
-        assert (s["visits_internal"], s["visits_leaf"]) == (int(visits[0]), int(visits[1]))
-        assert s["algorithmic_bytes"] > 0
+        assert (s["visits_internal"], s["visits_leaf"]) == exact
+        assert s["algorithmic_bytes"] > 0 and s["leaf_lookups"] == 0
         off, ids = tree.query_boxes(q, mode, rtb.RT_UNSORTED)
         assert np.array_equal(off, want[0]) and np.array_equal(sort_segments(off, ids), want[1])
         off, ids = tree.query_boxes(q, mode, rtb.RT_COUNT_ONLY)
@@ -282,6 +294,43 @@ def test_pipelined_call_equals_single_batch(rtb, flags):
             assert csr_equal(single, ref)
 
 
+def test_counts32_result_and_failed_call_leaves_the_handle_usable(rtb, monkeypatch):
+    """RT_RESULT_COUNTS32 delivers 32-bit hits per query (whose prefix sums are the offsets) with the
+    same ids, single batch and pipelined.  A call that fails in the middle of its pipeline (here: the
+    pinned id buffer is not allowed to grow) reports RT_E_NOMEM, and the next call on the handle is
+    answered as if nothing had happened."""
+    n, nq = 60000, 47003
+    pts = rtb.workloads.uniform_points(n, seed=21)
+    q = rtb.workloads.cube_queries(nq, n, seed=22)
+    q[2000:2030, 1] += 0.2
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+        tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, 0)
+        off, ids = tree.query_boxes(q)
+        for batch in (0, 5000):
+            tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, batch)
+            counts, ids32 = tree.query_boxes(q, flags=rtb.RT_RESULT_COUNTS32)
+            assert counts.dtype == np.uint32 and np.array_equal(np.cumsum(counts, dtype=np.uint64), off[1:])
+            assert np.array_equal(ids32, ids)
+            counts, none = tree.query_boxes(q, flags=rtb.RT_RESULT_COUNTS32 | rtb.RT_COUNT_ONLY)
+            assert np.array_equal(np.cumsum(counts, dtype=np.uint64), off[1:]) and none.size == 0
+        # values the planner cannot work with are refused, not divided by
+        for bad in (1, 7, 4095):
+            with pytest.raises(rtb.RtError) as e:
+                tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, bad)
+            assert e.value.code == rtb.capi.RT_E_INVALID
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:  # a fresh handle: no pinned ids yet
+        tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, 5000)
+        monkeypatch.setenv("RTB_HOST_IDS_LIMIT", str(len(ids) // 3))
+        with pytest.raises(rtb.RtError) as e:
+            tree.query_boxes(q)
+        assert e.value.code == rtb.capi.RT_E_NOMEM
+        monkeypatch.delenv("RTB_HOST_IDS_LIMIT")
+        for _ in range(2):
+            assert csr_equal(tree.query_boxes(q), (off, ids))
+        tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, 0)
+        assert csr_equal(tree.query_boxes(q), (off, ids))
+
+
 def _boundary_queries(pts, rng, n):
     """query boxes whose faces pass exactly through data points (closed intervals: those points are hits)"""
     a = pts[rng.integers(0, len(pts), n)]
@@ -427,9 +476,10 @@ def test_any_hit_is_the_abort_semantics(rtb, kind):
     with rtb.RTree(kind).insert(keys).flatten_device().upload(0) as tree:
         for quantised in (1, 0):
             tree.set_option(rtb.RT_OPT_QUANTISED, quantised)
-            for batch in (0, 2500):
+            for batch in (0, 4096):
                 tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, batch)
                 off, ids = tree.query_boxes(q, mode, rtb.RT_ANY_HIT)
+                assert tree.stats()["batches"] == (2 if batch else 1)
                 assert ids.size == 0 and np.array_equal(np.diff(off.astype(np.int64)), want.astype(np.int64))
         with pytest.raises(rtb.RtError):
             tree.query_boxes(q, mode, rtb.RT_ANY_HIT | rtb.RT_COLLECT_VISITS)

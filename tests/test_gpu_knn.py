@@ -52,6 +52,27 @@ def test_knn_vs_reference_search_and_brute_force(rtb):
         assert np.all(got[1][:300, 0][:300] >= 0) and np.all(got[1][:300, 0] == 0.0)   # the data points themselves
 
 
+@pytest.mark.parametrize("kind", [6, 10, 11, 3, 7, 5, 9])
+def test_knn_on_every_float32_tree_kind(rtb, kind):
+    """every float32 tree kind the engine accepts answers kNN -- 8-D with 16-wide blocks (BASELINE
+    config 4's kind, QuadraticSplit), 1-D, 4-D, 2-D points, 2-D / 3-D box keys, QuadraticSplit 3-D --
+    bit-exact against the reference's search() with the oracle/knn.h functors and against brute force"""
+    scalar, dim, is_box, _ = O.KINDS[kind]
+    assert scalar == O.F32
+    rng = np.random.default_rng(400 + kind)
+    n, nq = 30000, 6000
+    c = rng.random((n, dim)).astype(np.float32)
+    keys = np.stack([c, c + rng.uniform(0, 0.02, (n, dim)).astype(np.float32)], axis=1) if is_box else c
+    keys = np.ascontiguousarray(keys, np.float32)
+    q = rng.uniform(-0.1, 1.1, (nq, dim)).astype(np.float32)
+    q[:200] = c[:200]
+    ref = O.RefTree(kind).insert(keys)
+    with rtb.RTree(kind).insert(keys).flatten_device().upload(0) as tree:
+        for k in (1, 8, 32):
+            assert same(tree.query_knn(q, k), ref.search_knn(q, k))
+        assert same(tree.query_knn(q[:200], 7), O.oracle_brute_knn(keys, is_box, None, dim, q[:200], 7))
+
+
 def test_knn_edge_cases(rtb):
     rng = np.random.default_rng(5)
     pts = rng.random((5, 3)).astype(np.float32)               # root is a leaf, fewer keys than k

@@ -108,16 +108,18 @@ def test_rays_need_a_3d_f32_tree(rtb):
 
 
 def test_pipelined_ray_batches_equal_single_batch(rtb):
-    """closest / any calls with a host result are cut into batches whose copies overlap the
-    traversal of their neighbours; results and hit counts equal the unpipelined call and the
-    reference's search()"""
+    """ray calls with a host result are cut into batches whose copies overlap the traversal of their
+    neighbours (closest / any: one kernel per batch; all-hits: the two-phase CSR pipeline); results,
+    hit counts and visit counters equal the unpipelined call and the reference's search()"""
     boxes = rtb.workloads.triangle_aabbs(rtb.workloads.teapot_triangles(1.0))
     rays = rtb.workloads.random_rays(50_003, boxes, seed=45, tmax=1e30)
     ref = O.RefTree(5).insert(boxes)
     want_t, want_id = ref.search_rays(rays, O.RAY_CLOSEST)
     want_any = ref.search_rays(rays, O.RAY_ANY)
+    want_all = ref.search_rays(rays, O.RAY_ALL)
     with rtb.RTree(5).insert(boxes).flatten_device().upload(0) as tree:
-        for batch in (0, 2000, 3501, 10000):
+        visits = {}
+        for batch in (0, 4096, 5001, 10000):
             tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, batch)
             for _ in range(2):
                 r = np.ascontiguousarray(rays)
@@ -127,3 +129,16 @@ def test_pipelined_ray_batches_equal_single_batch(rtb):
                 t, tid = tree.query_rays(rays, rtb.RT_RAY_CLOSEST)
                 assert np.array_equal(t.view(np.uint32), want_t.view(np.uint32)) and np.array_equal(tid, want_id)
                 assert np.array_equal(tree.query_rays(rays, rtb.RT_RAY_ANY), want_any)
+                assert csr_equal(tree.query_rays(rays, rtb.RT_RAY_ALL_HITS), want_all)
+                assert tree.stats()["batches"] == (max(1, len(r) // (2 * batch)) if batch else 1)
+                off, none = tree.query_rays(rays, rtb.RT_RAY_ALL_HITS, rtb.RT_COUNT_ONLY)
+                assert np.array_equal(off, want_all[0]) and none.size == 0
+            # the visit counters exist for every mode and do not depend on how the call was cut
+            for mode in (rtb.RT_RAY_ALL_HITS, rtb.RT_RAY_CLOSEST, rtb.RT_RAY_ANY):
+                tree.query_rays(rays, mode, rtb.RT_COLLECT_VISITS)
+                s = tree.stats()
+                seen = (s["visits_internal"], s["visits_leaf"], s["algorithmic_bytes"])
+                assert seen[0] >= len(rays) and seen[2] > 0
+                assert visits.setdefault(mode, seen) == seen
+        # pruning and the first-hit abort visit fewer nodes than collecting every hit
+        assert visits[rtb.RT_RAY_ANY][0] <= visits[rtb.RT_RAY_CLOSEST][0] <= visits[rtb.RT_RAY_ALL_HITS][0]
