@@ -89,6 +89,19 @@ extern "C" {
                                      redundant): 4 instead of 8 bytes per query cross PCIe.  rt_hits.offsets
                                      is then NULL; ids are laid out exactly as without the flag            */
 
+#define RT_STRICT_OVERLAP 0x100u   /* rt_query_boxes: filter with the reference's N-D geometry_traits<aabb>::
+                                     is_overlap(aabb, aabb) (include/RTree/aabb.hpp:225-236), whose inequalities
+                                     are STRICT -- boxes that only touch do not overlap -- instead of the closed
+                                     overlap of the reference's sample / test / README.  Applies to the node
+                                     filter and to box keys under RT_INTERSECTS; point keys keep
+                                     is_overlap(aabb, point) = is_inside (closed), RT_CONTAINS its containment
+                                     test.  As in the reference this filter is NOT conservative for keys on a
+                                     face of the query box: such a key is found only if the bounds above it
+                                     overlap the query strictly, i.e. the hit set depends on the tree -- the
+                                     engine returns exactly what the reference's search() returns on the same
+                                     tree with these functors.  1-D trees: no effect (their is_overlap is closed,
+                                     aabb.hpp:147-159).  Runs on the float blocks.                          */
+
 /* An id slot that holds no entry.  Ids / value counts must stay below it.            */
 #define RT_INVALID_ID 0xFFFFFFFFu
 

@@ -9,6 +9,9 @@ extern "C" {
 
 enum { ORACLE_F32 = 0, ORACLE_F64 = 1, ORACLE_I32 = 2 };
 enum { ORACLE_MODE_POINT_IN_BOX = 0, ORACLE_MODE_INTERSECTS = 1, ORACLE_MODE_CONTAINS = 2 };
+/* OR-ed into the mode: filter with the reference's own is_overlap(aabb, aabb) (strict for N-D,
+ * include/RTree/aabb.hpp:225-236) instead of the closed overlap; see RT_STRICT_OVERLAP */
+enum { ORACLE_MODE_STRICT = 0x100 };
 enum { ORACLE_RAY_ALL = 0, ORACLE_RAY_CLOSEST = 1, ORACLE_RAY_ANY = 2 };
 
 /* The four vectors of flatten_result_t (include/RTree/rtree.hpp:852-870) as arrays. */

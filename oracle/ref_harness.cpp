@@ -47,7 +47,11 @@ enum
 {
   MODE_POINT_IN_BOX = 0,
   MODE_INTERSECTS = 1,
-  MODE_CONTAINS = 2
+  MODE_CONTAINS = 2,
+  // OR-ed in: the node filter, and the key test of box keys under MODE_INTERSECTS, is the reference's
+  // own geometry_traits<aabb>::is_overlap (include/RTree/aabb.hpp:225-236: strict for N-D boxes;
+  // :147-159: closed in 1-D; is_overlap(aabb, point) = is_inside, :219-223)
+  MODE_STRICT = 0x100
 };
 enum
 {
@@ -218,14 +222,18 @@ struct TreeImpl : ITree
   }
 
   // leaf predicates -----------------------------------------------------------
-  static bool leaf_hit(box const& q, point const& k, int /*mode*/)
+  static bool leaf_hit(box const& q, point const& k, int mode)
   {
+    if (mode & MODE_STRICT)
+      return er::geometry_traits<box>::is_overlap(q, k); // = is_inside for a point (aabb.hpp:219-223)
     // a3: the reference's own predicate
     return er::geometry_traits<box>::is_inside(q, k);
   }
   static bool leaf_hit(box const& q, box const& k, int mode)
   {
-    if (mode == MODE_CONTAINS)
+    if (mode == (MODE_INTERSECTS | MODE_STRICT))
+      return er::geometry_traits<box>::is_overlap(q, k);
+    if ((mode & ~MODE_STRICT) == MODE_CONTAINS)
     {
       for (unsigned d = 0; d < D; ++d)
       {
@@ -247,8 +255,11 @@ struct TreeImpl : ITree
   template <typename Emit>
   void one_box_query(box const& q, int mode, Emit&& emit) const
   {
-    auto filter = [&q](box const& b) -> int
+    const bool strict = (mode & MODE_STRICT) != 0;
+    auto filter = [&q, strict](box const& b) -> int
     {
+      if (strict)
+        return er::geometry_traits<box>::is_overlap(b, q) ? 1 : 0;
       for (unsigned d = 0; d < D; ++d)
       {
         if (A::hi(b, d) < A::lo(q, d) || A::lo(b, d) > A::hi(q, d))

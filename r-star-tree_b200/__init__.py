@@ -21,7 +21,7 @@ from . import capi, host, sharding, workloads  # noqa: F401
 from .capi import (DeviceTree, RtError, RT_POINT_IN_BOX, RT_INTERSECTS, RT_CONTAINS,  # noqa: F401
                    RT_RAY_ALL_HITS, RT_RAY_CLOSEST, RT_RAY_ANY, RT_QUERIES_ON_DEVICE,
                    RT_RESULT_ON_DEVICE, RT_UNSORTED, RT_COUNT_ONLY, RT_COLLECT_VISITS,
-                   RT_NO_REORDER, RT_ANY_HIT, RT_RESULT_COUNTS32, RT_INVALID_ID, RT_OPT_PIPELINE_BATCH, RT_OPT_QUERY_CHUNK,
+                   RT_NO_REORDER, RT_ANY_HIT, RT_RESULT_COUNTS32, RT_STRICT_OVERLAP, RT_INVALID_ID, RT_OPT_PIPELINE_BATCH, RT_OPT_QUERY_CHUNK,
                    RT_OPT_WORK_RANGES, RT_OPT_QUANTISED)
 from .host import RTree, DeviceImage, KINDS  # noqa: F401
 

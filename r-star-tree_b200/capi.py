@@ -24,6 +24,7 @@ RT_RAY_ALL_HITS, RT_RAY_CLOSEST, RT_RAY_ANY = 0, 1, 2
 RT_QUERIES_ON_DEVICE, RT_RESULT_ON_DEVICE, RT_UNSORTED = 0x1, 0x2, 0x4
 RT_COUNT_ONLY, RT_COLLECT_VISITS, RT_NO_REORDER, RT_ANY_HIT = 0x8, 0x10, 0x20, 0x40
 RT_RESULT_COUNTS32 = 0x80
+RT_STRICT_OVERLAP = 0x100
 RT_INVALID_ID = 0xFFFFFFFF
 RT_OPT_PIPELINE_BATCH, RT_OPT_QUERY_CHUNK, RT_OPT_WORK_RANGES, RT_OPT_TRAVERSE_GRID = 1, 2, 3, 4
 RT_OPT_QUANTISED = 5

@@ -33,7 +33,7 @@ struct BoxCall
 {
   rtb::box_launch_fn launch;
   size_t query_stride; // bytes per query
-  bool on_device, keep_on_device, count_only, collect, sorted, reorder, two_pass, pipelined, any_hit, counts32;
+  bool on_device, keep_on_device, count_only, collect, sorted, reorder, two_pass, pipelined, any_hit, counts32, strict;
 };
 
 struct Batch
@@ -71,7 +71,7 @@ int box_issue_count(rt_tree* t, const BoxCall& c, Batch& b)
   if (!c.on_device)
     RT_CUDA(s.d_queries.reserve(query_bytes ? query_bytes : 16));
   // quantised trees of dim <= 3 take their queries packed: in processing order, on the tree's grid
-  const bool packed = t->use_quant && t->dev.qblocks != nullptr && t->desc.dim <= 3;
+  const bool packed = t->use_quant && !c.strict && t->dev.qblocks != nullptr && t->desc.dim <= 3;
   if (packed)
     RT_CUDA(s.d_packed.reserve((size_t)(n ? n : 1) * sizeof(uint4)));
   else if (reorder)
@@ -158,8 +158,9 @@ int box_issue_count(rt_tree* t, const BoxCall& c, Batch& b)
   rtb::BoxLaunch& L = b.L;
   std::memset(&L, 0, sizeof L);
   L.tree = t->dev;
-  if (!t->use_quant)
+  if (!t->use_quant || c.strict) // the strict filter is not conservative for the quantised grid: float blocks
     L.tree.qblocks = nullptr;
+  L.strict = c.strict ? 1u : 0u;
   L.queries = d_q;
   L.packed = packed ? s.d_packed.as<uint4>() : nullptr;
   L.order = b.d_order;
@@ -526,6 +527,7 @@ int rt_query_boxes(rt_tree* t, const void* boxes, uint64_t n, uint32_t mode, uin
   c.reorder = (flags & RT_NO_REORDER) == 0;
   c.two_pass = c.collect || c.count_only;
   c.counts32 = (flags & RT_RESULT_COUNTS32) != 0 && !c.keep_on_device;
+  c.strict = (flags & RT_STRICT_OVERLAP) != 0;
   c.pipelined = false;
   if ((rc = run_box_call(t, c, boxes, n, out)) != RT_OK)
   {

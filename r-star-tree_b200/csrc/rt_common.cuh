@@ -108,6 +108,7 @@ struct BoxLaunch
   unsigned long long* confirm_stats; // [0] leaf candidates looked up on the float records (COUNT_STATS)
   uint32_t sorted;                  // 0: keep traversal order
   uint32_t stop_at_first;           // PASS_COUNT: abort a query at its first hit (RT_ANY_HIT): counts are 0 / 1
+  uint32_t strict;                  // RT_STRICT_OVERLAP: the reference's strict is_overlap as the filter (float blocks)
   int grid;                         // 0: fill the GPU; > 0: exactly; < 0: fill, less -grid CTAs per SM
   cudaStream_t stream;
 };

@@ -71,13 +71,18 @@ __device__ __forceinline__ void claim_stash_slab(const BoxLaunch& p, int lane, u
 // (BoxLaunch::packed) -- one 128-bit load per query instead of an index, six floats and six
 // quantisations per warp.
 //
-// __syncwarp() inside the traversal loop.  The stack is written and read by different lanes, so the
-// loop needs the lanes to stay together.  They do: every step has full-mask ballots between the pop
-// and the push, and from the last ballot to the next pop there is no divergent branch (the push is
-// predicated, the leaf branch is decided by a ballot result).  RTB_LOOP_SYNCWARP = 1 keeps the explicit
-// barriers (two issue slots per step); 0 relies on the ballots.
+// No __syncwarp() inside the traversal loop (RTB_LOOP_SYNCWARP = 0).  The stack is written and read by
+// different lanes, so the loop needs the lanes of a warp to execute it together -- and they do: the
+// whole warp enters a step converged (the loop condition is a ballot result), the pop is one LDS for
+// all lanes, every step has two full-mask vote.sync between the pop and the push, the push is a
+// predicated STS (no branch), and the only divergent code (the leaf section's `if (lane has a hit)`)
+// sits inside reconvergence barriers (BSSY / BSYNC in the SASS, profiles/r2_*_loop.sass) that close
+// before the next pop.  A converged warp's shared-memory instructions are executed in program order
+// by the LSU, so pop -> push -> pop needs no further barrier; the two explicit ones cost two issue
+// slots per step (3.6 % of the kernel, measured).  RTB_LOOP_SYNCWARP = 1 puts them back (`make
+// variants` builds that as librtree_b200_sync.so for comparison).  The per-query barriers stay.
 #ifndef RTB_LOOP_SYNCWARP
-#define RTB_LOOP_SYNCWARP 1
+#define RTB_LOOP_SYNCWARP 0
 #endif
 #if RTB_LOOP_SYNCWARP
 #define RTB_LOOP_SYNC() __syncwarp()
@@ -99,10 +104,15 @@ __device__ __forceinline__ void claim_stash_slab(const BoxLaunch& p, int lane, u
 #define RTB_PROGRESSIVE_ROWS 0
 #endif
 
-template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS, bool QUANT = false>
+// STRICT (RT_STRICT_OVERLAP, float blocks only): the node filter -- and the key test of box keys under
+// RT_INTERSECTS -- is the reference's N-D geometry_traits<aabb>::is_overlap(aabb, aabb)
+// (include/RTree/aabb.hpp:225-236, less_than :238-248): boxes that only touch do not overlap.  Point
+// keys keep is_overlap(aabb, point) = is_inside (aabb.hpp:219-223), RT_CONTAINS its containment test.
+template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS, bool QUANT = false, bool STRICT = false>
 __global__ void __launch_bounds__(TRAVERSE_THREADS, QUANT ? 8 : 1) // quantised kernels: 32 registers, 64 warps per SM
 box_traverse_kernel(const BoxLaunch p)
 {
+  static_assert(!(QUANT && STRICT), "the strict filter runs on the float blocks");
   static_assert(!QUANT || (std::is_same<S, float>::value && !BOXKEY),
                 "the quantised image exists for float32 point-keyed trees");
   constexpr int G = 32 / W;
@@ -113,12 +123,14 @@ box_traverse_kernel(const BoxLaunch p)
   const int warp = threadIdx.x >> 5;
   const int slot = lane % W;
   const uint32_t grp = lane / W;
-  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t lt_mask = (1u << lane) - 1u;
+  asm volatile("" : "+r"(lt_mask)); // kept in its register: ptxas otherwise re-derives it from %tid in the leaf path
 
   // per warp: the hit buffer, G words holding the null node, the stack (32-bit shared addresses;
   // the hit buffer sits at a constant distance below the stack so it needs no register of its own)
   const uint32_t stack_cap = 32u * p.tree.num_levels;
-  const uint32_t warp_mem = smem_addr(smem + warp * (HIT_BUF + G + stack_cap));
+  uint32_t warp_mem = smem_addr(smem + warp * (HIT_BUF + G + stack_cap));
+  asm volatile("" : "+r"(warp_mem)); // likewise: one register for the hit buffer, the stack and the null words
   const uint32_t stack = warp_mem + (HIT_BUF + G) * 4u;
   constexpr uint32_t HITBUF_BELOW = (HIT_BUF + G) * 4u; // hit buffer = stack - HITBUF_BELOW
   // group g pops the word at stack_pop + 4 * sp, i.e. stack index sp - G + g: with fewer than G
@@ -309,7 +321,12 @@ box_traverse_kernel(const BoxLaunch p)
 #pragma unroll
           for (int d = 0; d < D; ++d)
           {
-            if (BOXKEY && CONTAINS)
+            if (STRICT && (!is_leaf || (BOXKEY && !CONTAINS)))
+            {
+              // the reference's strict overlap: false as soon as one axis has q.min >= hi or lo >= q.max
+              hit = hit && !(qlo[d] >= hi[d]) && !(lo[d] >= qhi[d]);
+            }
+            else if (BOXKEY && CONTAINS)
             {
               // leaf: key box inside the query box; internal: closed overlap
               const S a = is_leaf ? lo[d] : hi[d];
@@ -426,7 +443,7 @@ box_traverse_kernel(const BoxLaunch p)
               if (buffered)
               {
                 if (at < HIT_BUF)
-                  sts_u32(stack - HITBUF_BELOW + at * 4u, link);
+                  sts_u32(warp_mem + at * 4u, link);
                 else if (PASS == PASS_STASH && at < slab_left)
                   p.stash[slab_pos + at] = link; // beyond the hit buffer: straight into the warp's slab,
                                                  // at its final place there (sorted after the gather)
@@ -467,7 +484,7 @@ box_traverse_kernel(const BoxLaunch p)
         {
           if (slab_left >= count)
           {
-            uint32_t v = ((uint32_t)lane < count) ? lds_u32(stack - HITBUF_BELOW + lane * 4u) : RT_INVALID_ID;
+            uint32_t v = ((uint32_t)lane < count) ? lds_u32(warp_mem + lane * 4u) : RT_INVALID_ID;
             if (p.sorted)
               v = warp_sort32(v, lane, count);
             if ((uint32_t)lane < count)
@@ -481,7 +498,7 @@ box_traverse_kernel(const BoxLaunch p)
         {
           // a list that outgrew the hit buffer but not the slab: ids HIT_BUF.. are in the slab
           // already (every one of them had at < slab_left), the first HIT_BUF join them
-          p.stash[slab_pos + lane] = lds_u32(stack - HITBUF_BELOW + lane * 4u);
+          p.stash[slab_pos + lane] = lds_u32(warp_mem + lane * 4u);
           where = (uint32_t)slab_pos;
           slab_pos += count;
           slab_left -= count;
@@ -500,7 +517,7 @@ box_traverse_kernel(const BoxLaunch p)
       {
         if (buffered)
         {
-          uint32_t v = ((uint32_t)lane < count) ? lds_u32(stack - HITBUF_BELOW + lane * 4u) : RT_INVALID_ID;
+          uint32_t v = ((uint32_t)lane < count) ? lds_u32(warp_mem + lane * 4u) : RT_INVALID_ID;
           v = warp_sort32(v, lane, count);
           if ((uint32_t)lane < count && (uint32_t)lane < expect)
             p.ids[out_base + lane] = v;
@@ -524,18 +541,24 @@ box_traverse_kernel(const BoxLaunch p)
   }
 }
 
-template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS, bool QUANT = false>
+template <typename S, int D, int W, bool BOXKEY, bool CONTAINS, uint32_t PASS, bool QUANT = false, bool STRICT = false>
 cudaError_t launch_box_pass(const BoxLaunch& p)
 {
   // the (dim, width) pairs of quant_supported() in rt_quant.cu
   constexpr bool CAN_QUANT = std::is_same<S, float>::value && !BOXKEY
                              && ((D == 2 && W == 8) || (D == 3 && W == 8) || (D == 8 && W == 16));
-  if constexpr (CAN_QUANT && !QUANT)
+  if constexpr (CAN_QUANT && !QUANT && !STRICT)
   {
     if (p.tree.qblocks != nullptr)
       return launch_box_pass<S, D, W, BOXKEY, CONTAINS, PASS, true>(p);
   }
-  auto kernel = box_traverse_kernel<S, D, W, BOXKEY, CONTAINS, PASS, QUANT>;
+  // (a 1-D tree's is_overlap is closed in the reference, include/RTree/aabb.hpp:147-159: nothing to do)
+  if constexpr (!STRICT && !QUANT && D > 1)
+  {
+    if (p.strict)
+      return launch_box_pass<S, D, W, BOXKEY, CONTAINS, PASS, false, true>(p);
+  }
+  auto kernel = box_traverse_kernel<S, D, W, BOXKEY, CONTAINS, PASS, QUANT, STRICT>;
   size_t smem = traverse_smem_bytes(p.tree.num_levels, W);
 #if RTB_STAGE_TOP
   if (QUANT)

@@ -19,6 +19,7 @@ REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_oracle.so")
 F32, F64, I32 = 0, 1, 2
 SCALAR_DTYPES = {F32: np.float32, F64: np.float64, I32: np.int32}
 MODE_POINT_IN_BOX, MODE_INTERSECTS, MODE_CONTAINS = 0, 1, 2
+MODE_STRICT = 0x100  # OR-ed in: the reference's own (strict) is_overlap as the filter, see RT_STRICT_OVERLAP
 RAY_ALL, RAY_CLOSEST, RAY_ANY = 0, 1, 2
 
 # kind -> (scalar, dim, key_is_box, max_entries); must match make_tree() in

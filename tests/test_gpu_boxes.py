@@ -485,6 +485,41 @@ def test_any_hit_is_the_abort_semantics(rtb, kind):
             tree.query_boxes(q, mode, rtb.RT_ANY_HIT | rtb.RT_COLLECT_VISITS)
 
 
+@pytest.mark.parametrize("kind", [8, 13, 4, 5, 7, 2, 6, 0])
+def test_strict_overlap_flag_equals_the_reference_traits(rtb, kind):
+    """RT_STRICT_OVERLAP: the node filter (and the key test of box keys) is the reference's own
+    geometry_traits<aabb>::is_overlap(aabb, aabb) (include/RTree/aabb.hpp:225-236) -- strict
+    inequalities, so touching boxes do not overlap; 1-D trees: closed, as in the reference.  On lattice
+    coordinates, against the reference's search() with those traits on the same tree, for int32 /
+    float32 / float64, point and box keys, 8-wide and 16-wide blocks, pipelined and not."""
+    scalar, dim, is_box, _ = O.KINDS[kind]
+    dt = O.SCALAR_DTYPES[scalar]
+    rng = np.random.default_rng(500 + kind)
+    n, nq = 20000, 9000
+    side = {1: 15000, 2: 130, 3: 26, 8: 4}[dim]
+    c = rng.integers(0, side, (n, dim))
+    keys = np.stack([c, c + rng.integers(0, 3, (n, dim))], axis=1).astype(dt) if is_box else c.astype(dt)
+    lo = rng.integers(-1, side, (nq, dim))
+    q = np.stack([lo, lo + rng.integers(0, 4, (nq, dim))], axis=1).astype(dt)
+    ref = O.RefTree(kind).insert(keys)
+    flat = ref.flatten()
+    image = rtb.DeviceImage.from_flat(kind, flat.leaf_level, flat.nodes, flat.bounds, flat.children, flat.data)
+    modes = [(rtb.RT_INTERSECTS, O.MODE_INTERSECTS), (rtb.RT_CONTAINS, O.MODE_CONTAINS)] if is_box \
+        else [(rtb.RT_POINT_IN_BOX, O.MODE_POINT_IN_BOX)]
+    with image.upload(0) as tree:
+        for mode, omode in modes:
+            want = ref.search_boxes(q, omode | O.MODE_STRICT)
+            closed = ref.search_boxes(q, omode)
+            for batch in (0, 4096):
+                tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, batch)
+                assert csr_equal(tree.query_boxes(q, mode, rtb.RT_STRICT_OVERLAP), want)
+                assert csr_equal(tree.query_boxes(q, mode), closed)        # and the default is untouched
+            off, none = tree.query_boxes(q, mode, rtb.RT_STRICT_OVERLAP | rtb.RT_COUNT_ONLY)
+            assert np.array_equal(off, want[0])
+            if dim > 1:
+                assert want[1].size < closed[1].size
+
+
 @pytest.mark.parametrize("kind,dim", [(4, 3), (3, 2)])
 def test_float_lattice_known_answer(rtb, kind, dim):
     """the reference's Flatten known-answer test (test/rtree.cpp:410-467: a closed range over integer

@@ -25,6 +25,10 @@ def load(name):
     return z, O.Flat.load(z)
 
 
+def csr_same(a, b):
+    return np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
 def test_oracle_library_is_built():
     assert O.have_oracle(), "run `make -C oracle` (or __graft_entry__.build())"
 
@@ -162,6 +166,43 @@ def test_restatement_matches_reference_search_box_keys(mode):
     assert np.array_equal(ro, oo) and np.array_equal(ri, oi)
     assert np.array_equal(ro, bo) and np.array_equal(ri, bi)
     assert ri.size > 0
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", [8, 13, 4, 5, 7, 2, 6, 0])
+def test_strict_overlap_restatement_matches_the_reference_traits(kind):
+    """MODE_STRICT: search() filtered by the reference's OWN geometry_traits<aabb>::is_overlap
+    (include/RTree/aabb.hpp:225-236; strict for N-D boxes, closed in 1-D) instead of the closed overlap
+    of its sample / test.  Lattice coordinates make touching boxes and keys on query faces the common
+    case; the restatement walks the reference's flatten() and must deliver the same lists (this filter
+    is not conservative for keys on a face, so the hit set depends on the tree: same tree, same answer)."""
+    scalar, dim, is_box, _ = O.KINDS[kind]
+    dt = O.SCALAR_DTYPES[scalar]
+    rng = np.random.default_rng(500 + kind)
+    n, nq = 4000, 3000
+    side = {1: 3000, 2: 60, 3: 16, 8: 3}[dim]
+    c = rng.integers(0, side, (n, dim))
+    if is_box:
+        keys = np.stack([c, c + rng.integers(0, 3, (n, dim))], axis=1).astype(dt)
+    else:
+        keys = c.astype(dt)
+    lo = rng.integers(-1, side, (nq, dim))
+    q = np.stack([lo, lo + rng.integers(0, 4, (nq, dim))], axis=1).astype(dt)
+    ref = O.RefTree(kind).insert(keys)
+    flat = ref.flatten()
+    base = O.MODE_INTERSECTS if is_box else O.MODE_POINT_IN_BOX
+    strict = ref.search_boxes(q, base | O.MODE_STRICT)
+    closed = ref.search_boxes(q, base)
+    assert csr_same(O.oracle_query_boxes(flat, q, base | O.MODE_STRICT), strict)
+    # never more than the closed filter finds; in 1-D the reference's is_overlap IS closed
+    assert np.all(np.diff(strict[0].astype(np.int64)) <= np.diff(closed[0].astype(np.int64)))
+    if dim == 1:
+        assert csr_same(strict, closed)
+    else:
+        assert strict[1].size < closed[1].size
+    if is_box:
+        assert csr_same(O.oracle_query_boxes(flat, q, O.MODE_CONTAINS | O.MODE_STRICT),
+                        ref.search_boxes(q, O.MODE_CONTAINS | O.MODE_STRICT))
 
 
 @needs_ref
