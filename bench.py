@@ -372,15 +372,13 @@ class Ctx:
             return None
         if ref_tree is None:
             return {"checked": False, "why": "oracle/_ref was not built"}
-        per_rank = []
         threads = host_threads()
-        for r, (count, off, ids) in enumerate(parts):
-            q = my_queries_prefix if r == 0 else regenerate(r, count)
-            want = ref_tree.search_boxes(q, threads=threads)
-            ok = bool(np.array_equal(off, want[0]) and np.array_equal(ids, want[1]))
-            per_rank.append({"rank": r, "checked_queries": int(count), "hits": int(len(want[1])), "bit_exact": ok})
-            if not ok:
-                log("[bench] PARITY FAILURE (%s): rank %d differs from the reference search()" % (what, r))
+        per_rank = self.rtb.sharding.check_rank_prefixes(
+            parts, lambda q: ref_tree.search_boxes(q, threads=threads),
+            lambda r, count: my_queries_prefix if r == 0 else regenerate(r, count))
+        for entry in per_rank:
+            if not entry["bit_exact"]:
+                log("[bench] PARITY FAILURE (%s): rank %d differs from the reference search()" % (what, entry["rank"]))
                 self.parity_ok = False
         return {"against": "reference RTree::search() (oracle/_ref), sorted ids per query",
                 "per_rank": per_rank, "bit_exact_vs_reference_search": all(p["bit_exact"] for p in per_rank)}
@@ -750,6 +748,7 @@ def section_knn(cx, gpu_tree, ref_tree, points_n):
 
 # ---------------------------------------------------------------------------------------
 def main():
+    t_start = time.time()
     args = parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -1041,6 +1040,7 @@ def main():
             "config4": c4_section,
             "config5": c5_section,
             "knn": knn_section,
+            "host": {"threads": host_threads(), "wall_s": round(time.time() - t_start, 1)},
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

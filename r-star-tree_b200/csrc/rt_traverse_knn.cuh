@@ -20,7 +20,8 @@
 //     nearest child, found with a butterfly over the node's lanes;
 //   * the k best pairs are kept SORTED across the lanes (lane i holds the i-th best, k <= 32): a
 //     candidate that beats the worst is inserted with one shuffle-up of the pairs behind it, the
-//     worst is simply lane k-1's pair, and the result needs no sort at the end.  (Round 1 kept them
+//     worst is simply lane k-1's pair, and the result needs no sort at the end.  The candidates of a
+//     step are offered nearest first (one warp min-reduction each).  (Round 1 kept them
 //     unsorted, found the worst with two warp reductions per accepted candidate and sorted 64-bit
 //     pairs over the warp per query: 13 k instructions per query, now about a third.)
 #pragma once
@@ -154,15 +155,23 @@ knn_traverse_kernel(const KnnLaunch p)
           sp8 += __popc(m_push) * 8u;
         }
 
-        // ---- leaf entries that beat the worst of the k best: inserted one at a time -----------------
-        uint32_t m_cand = __ballot_sync(0xFFFFFFFFu, valid && is_leaf && (d2b < wd || (d2b == wd && link < wi)));
+        // ---- leaf entries that beat the worst of the k best: inserted one at a time, nearest first ----
+        // (nearest first: every insertion tightens the bound as much as it can, so fewer of the step's
+        // later candidates still qualify, and the first one whose distance exceeds the bound ends the
+        // step -- 77 insertions per query in lane order at k = 8 on the config-2 tree)
+        bool cand = valid && is_leaf && (d2b < wd || (d2b == wd && link < wi));
+        uint32_t m_cand = __ballot_sync(0xFFFFFFFFu, cand);
         while (m_cand != 0)
         {
-          const int src = __ffs(m_cand) - 1;
-          m_cand &= m_cand - 1;
-          const uint32_t cd = __shfl_sync(0xFFFFFFFFu, d2b, src);
+          const uint32_t cd = __reduce_min_sync(0xFFFFFFFFu, cand ? d2b : 0xFFFFFFFFu);
+          if (cd > wd)
+            break; // no remaining candidate can beat the worst any more
+          const int src = __ffs(__ballot_sync(0xFFFFFFFFu, cand && d2b == cd)) - 1;
           const uint32_t ci = __shfl_sync(0xFFFFFFFFu, link, src);
-          if (cd < wd || (cd == wd && ci < wi)) // still better than the worst (warp-uniform)
+          if (lane == src)
+            cand = false;
+          m_cand &= ~(1u << src);
+          if (cd < wd || ci < wi) // (cd == wd here otherwise) still better than the worst: warp-uniform
           {
             // every pair behind the candidate's place moves up one lane, the lane at its place takes it
             const bool behind = bd > cd || (bd == cd && bi > ci);

@@ -68,3 +68,19 @@ def gather_csr(offsets, ids, dst=0, group=None):
     if rank != dst:
         return None
     return concat_csr(parts)
+
+
+def check_rank_prefixes(parts, reference_search, regenerate):
+    """Per-rank parity of a sharded run, on the rank that holds the checker.
+
+    parts[r] = (count, offsets[count + 1], ids) is what rank r's engine answered for the first
+    `count` queries of ITS batch (gathered with all_gather_object); `regenerate(r, count)` rebuilds
+    those queries from rank r's seed, `reference_search(queries)` -> (offsets, ids) is the checker
+    (the reference's RTree::search()).  Returns one dict per rank: bit_exact is true only when both
+    the offsets and the ids are identical."""
+    out = []
+    for r, (count, off, ids) in enumerate(parts):
+        want_off, want_ids = reference_search(regenerate(r, int(count)))
+        ok = bool(np.array_equal(np.asarray(off), want_off) and np.array_equal(np.asarray(ids), want_ids))
+        out.append({"rank": r, "checked_queries": int(count), "hits": int(len(want_ids)), "bit_exact": ok})
+    return out

@@ -58,10 +58,21 @@ def _worker(rank, world, port, out_path):
                flat["children"], flat["data"])
     off, ids = O.oracle_query_boxes(F, queries[begin:end])
     merged = rtb.sharding.gather_csr(off, ids, 0)
+    # per-rank parity as bench.py does it: every rank answers a batch of ITS OWN (seeded by its rank),
+    # sends the CSR of a prefix, and rank 0 regenerates each rank's queries and checks them all
+    def my_batch(r, count):
+        return rtb.workloads.cube_queries(count, n, seed=43 + 1000 * r)
+    mine = O.oracle_query_boxes(F, my_batch(rank, 300))
+    if rank == 1:
+        mine[1][5] ^= 1          # rank 1 "computes" one wrong id: it must be flagged, rank 0 must not
+    parts = [None] * world
+    dist.all_gather_object(parts, (200, mine[0][:201], mine[1][:int(mine[0][200])]))
     if rank == 0:
         full = O.oracle_query_boxes(F, queries)
         ok = np.array_equal(merged[0], full[0]) and np.array_equal(merged[1], full[1])
-        np.save(out_path, np.array([int(ok), int(got.nbytes), len(full[1])]))
+        verdict = rtb.sharding.check_rank_prefixes(parts, lambda q: O.oracle_query_boxes(F, q), my_batch)
+        flags = [int(v["bit_exact"]) for v in verdict]
+        np.save(out_path, np.array([int(ok), int(got.nbytes), len(full[1])] + flags))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -73,5 +84,6 @@ def test_two_rank_query_sharding_over_gloo(tmp_path):
         port = s.getsockname()[1]
     out = str(tmp_path / "result.npy")
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
-    ok, nbytes, hits = np.load(out)
+    ok, nbytes, hits, rank0_exact, rank1_exact = np.load(out)
     assert ok == 1 and nbytes > 0 and hits > 0
+    assert rank0_exact == 1 and rank1_exact == 0     # the corrupted rank is caught, the clean one passes
