@@ -513,7 +513,8 @@ def section_config4(cx, c4):
     h = c4_half_width(n)
 
     def make_queries(rank, count):
-        return W.mixture_queries(count, pts, h, seed=46 + 1000 * rank)
+        # (the generator draws all centres, then all jitters: a prefix is only a prefix of the FULL batch)
+        return W.mixture_queries(nq, pts, h, seed=46 + 1000 * rank)[:count]
     q = make_queries(cx.rank, nq)
     h_q = torch.from_numpy(q).pin_memory()
     d_q = h_q.to(cx.device)
