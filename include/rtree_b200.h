@@ -295,6 +295,11 @@ int rt_get_stats(const rt_tree* tree, rt_stats* out);
  *   are defined on).                                                                           */
 #define RT_OPT_QUANTISED 5u
 int rt_set_option(rt_tree* tree, uint32_t option, uint64_t value);
+/* How rt_query_boxes would cut a host-result call of n queries with RT_OPT_PIPELINE_BATCH =
+ * pipeline_batch: writes at most `capacity` batch sizes to sizes[] (NULL: none) and returns the
+ * number of batches, or RT_E_INVALID.  Pure host arithmetic (no device needed); values below the
+ * minimum of 4096 are taken as 4096 here, as the RTB_PIPELINE_BATCH environment override is.     */
+int64_t rt_plan_batches(uint64_t n, uint64_t pipeline_batch, uint64_t* sizes, uint64_t capacity);
 /* Device copy of the blocks, e.g. to broadcast the tree to peer GPUs.               */
 int rt_tree_device_blocks(const rt_tree* tree, void** device_ptr, uint64_t* bytes);
 int rt_tree_get_desc(const rt_tree* tree, rt_tree_desc* out);

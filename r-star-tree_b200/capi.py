@@ -33,7 +33,7 @@ SCALAR_DTYPES = {RT_F32: np.float32, RT_F64: np.float64, RT_I32: np.int32}
 
 # every symbol include/rtree_b200.h declares
 EXPORTS = ["rt_upload", "rt_query_boxes", "rt_query_rays", "rt_query_knn", "rt_refit", "rt_free", "rt_set_stream",
-           "rt_set_option", "rt_get_stats", "rt_tree_device_blocks", "rt_tree_get_desc", "rt_last_error",
+           "rt_set_option", "rt_plan_batches", "rt_get_stats", "rt_tree_device_blocks", "rt_tree_get_desc", "rt_last_error",
            "rt_abi_version", "rt_device_count"]
 
 
@@ -117,6 +117,8 @@ def lib():
         L.rt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.rt_set_option.restype = C.c_int
         L.rt_set_option.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
+        L.rt_plan_batches.restype = C.c_int64
+        L.rt_plan_batches.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]
         L.rt_get_stats.restype = C.c_int
         L.rt_get_stats.argtypes = [C.c_void_p, C.POINTER(RtStats)]
         L.rt_tree_device_blocks.restype = C.c_int
@@ -141,6 +143,16 @@ def _host_array(ptr, count, dtype):
         return np.zeros(0, dtype)
     buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
     return np.frombuffer(buf, dtype=dtype, count=count).copy()
+
+
+def plan_batches(n, pipeline_batch):
+    """the batch sizes rt_query_boxes cuts a host-result call of n queries into (host arithmetic only)"""
+    count = lib().rt_plan_batches(n, pipeline_batch, None, 0)
+    if count < 0:
+        _check(int(count))
+    sizes = (C.c_uint64 * max(1, count))()
+    lib().rt_plan_batches(n, pipeline_batch, sizes, count)
+    return [int(x) for x in sizes[:count]]
 
 
 class DeviceBuffer:

@@ -176,6 +176,7 @@ int box_issue_count(rt_tree* t, const BoxCall& c, Batch& b)
   L.deferred_count = &dc->deferred;
   L.big_list = s.d_big.as<uint32_t>();
   L.big_count = &dc->big;
+  L.max_list = &dc->max_list;
   L.work.cursors = s.d_cursors.as<unsigned int>();
   L.work.chunk = t->query_chunk;
   L.work.ranges = t->work_ranges;
@@ -266,10 +267,19 @@ int box_issue_write(rt_tree* t, const BoxCall& c, Batch& b, unsigned long long b
       ++b.launches;
     }
     // long lists -- spilled into the stash by the first traversal, or written by the second -- are sorted here
+    // (lists beyond 8192 ids together, by a global-memory network: needs a small table)
     if (c.sorted && (second || b.hc.big > 0))
+    {
+      void* long_scratch = nullptr;
+      if (b.hc.max_list > 8192)
+      {
+        RT_CUDA(s.d_long.reserve(rtb::long_sort_scratch_bytes(total)));
+        long_scratch = s.d_long.p;
+      }
       RT_CUDA(rtb::launch_sort_segments(s.d_big.as<uint32_t>(), &dc->big, (uint32_t)n,
                                         s.d_offsets.as<unsigned long long>(), s.d_ids.as<uint32_t>(), st,
-                                        &b.launches));
+                                        &b.launches, b.hc.max_list, long_scratch, total));
+    }
   }
   RT_CUDA(cudaEventRecord(b.ev[EV_FINISH], st));
 
@@ -490,6 +500,16 @@ int run_box_call(rt_tree* t, BoxCall& c, const void* boxes, uint64_t n, rt_hits*
 
 extern "C"
 {
+
+int64_t rt_plan_batches(uint64_t n, uint64_t pipeline_batch, uint64_t* sizes, uint64_t capacity)
+{
+  if (n >= 0xFFFFFFFFull)
+    return fail(RT_E_INVALID, "rt_plan_batches: at most 2^32-2 queries per call");
+  const std::vector<uint64_t> plan = plan_batches(n, pipeline_batch, false);
+  for (size_t k = 0; k < plan.size() && sizes != nullptr && k < capacity; ++k)
+    sizes[k] = plan[k];
+  return (int64_t)plan.size();
+}
 
 int rt_query_boxes(rt_tree* t, const void* boxes, uint64_t n, uint32_t mode, uint32_t flags, rt_hits* out)
 {

@@ -53,6 +53,7 @@ void fill_launch(rt_tree* t, Slot& s, const RayCall& c, const float* d_rays, uin
   L.offsets = s.d_offsets.as<unsigned long long>();
   L.big_list = s.d_big.as<uint32_t>();
   L.big_count = &dc->big;
+  L.max_list = &dc->max_list;
   L.t_out = t->d_ray_t.as<float>() + first;
   L.id_out = t->d_ray_id.as<uint32_t>() + first;
   L.any_out = t->d_ray_any.as<uint8_t>() + first;
@@ -273,9 +274,17 @@ int run_all_hits_pipelined(rt_tree* t, const RayCall& c, uint64_t per_batch, rt_
         RT_CUDA(rtb::launch_ray_kernel(b.L));
         ++b.launches;
         if (c.sorted)
+        {
+          void* long_scratch = nullptr;
+          if (b.hc.max_list > 8192)
+          {
+            RT_CUDA(s.d_long.reserve(rtb::long_sort_scratch_bytes(batch_total)));
+            long_scratch = s.d_long.p;
+          }
           RT_CUDA(rtb::launch_sort_segments(s.d_big.as<uint32_t>(), &s.d_counters.as<Counters>()->big, (uint32_t)b.n,
                                             s.d_offsets.as<unsigned long long>(), s.d_ids.as<uint32_t>(), bs,
-                                            &b.launches));
+                                            &b.launches, b.hc.max_list, long_scratch, batch_total));
+        }
       }
     }
     RT_CUDA(cudaEventRecord(b.ev[EV_FINISH], bs));
@@ -410,9 +419,17 @@ int run_rays_single(rt_tree* t, const RayCall& c, rt_ray_result* out)
       RT_CUDA(rtb::launch_ray_kernel(L));
       ++launches;
       if (c.sorted)
+      {
+        void* long_scratch = nullptr;
+        if (hc.max_list > 8192)
+        {
+          RT_CUDA(w.d_long.reserve(rtb::long_sort_scratch_bytes(total)));
+          long_scratch = w.d_long.p;
+        }
         RT_CUDA(rtb::launch_sort_segments(w.d_big.as<uint32_t>(), &dc->big, (uint32_t)n,
                                           w.d_offsets.as<unsigned long long>(), w.d_ids.as<uint32_t>(), st,
-                                          &launches));
+                                          &launches, hc.max_list, long_scratch, total));
+      }
     }
   }
   RT_CUDA(cudaEventRecord(ev[EV_FINISH], st));

@@ -103,6 +103,7 @@ struct BoxLaunch
   uint32_t* deferred_count;
   uint32_t* big_list;               // queries whose list must be sorted afterwards (STASH spills, WRITE)
   uint32_t* big_count;
+  uint32_t* max_list;               // longest list that will go to the segment sort (device counter, atomicMax)
   WorkRanges work;                  // cursors = MAX_WORK_RANGES entries; the rest is set by the launcher
   unsigned long long* visit_stats;  // [0] internal / [1] leaf visits, [3] loop steps (COUNT_STATS)
   unsigned long long* confirm_stats; // [0] leaf candidates looked up on the float records (COUNT_STATS)
@@ -138,6 +139,7 @@ struct RayLaunch
   uint32_t* ids;
   uint32_t* big_list;
   uint32_t* big_count;
+  uint32_t* max_list; // longest list that will go to the segment sort
   float* t_out;
   uint32_t* id_out;
   uint8_t* any_out;
@@ -199,10 +201,17 @@ cudaError_t launch_add_base(unsigned long long* offsets, uint64_t n, unsigned lo
 cudaError_t launch_gather_stash(const uint32_t* stash, const uint32_t* stash_pos,
                                 const unsigned long long* offsets, uint64_t n, uint32_t* ids,
                                 cudaStream_t stream, uint32_t* launches);
-// sort ids[offsets[q] .. offsets[q+1]) ascending for the queries in big_list
+// sort ids[offsets[q] .. offsets[q+1]) ascending for the queries in big_list.  Lists of up to 8192 ids
+// are sorted by one CTA each in shared memory.  `longest` = an upper bound of the longest list (the
+// counter the traversal keeps); when it exceeds 8192 the longer lists are sorted TOGETHER by a bitonic
+// network in global memory, one launch per network step over all their elements, so that one huge list
+// (a query covering much of the tree) gets the whole GPU instead of a single CTA.  `long_scratch` must
+// then hold long_sort_scratch_bytes(total ids of the batch) bytes.
+size_t long_sort_scratch_bytes(unsigned long long total_ids);
 cudaError_t launch_sort_segments(const uint32_t* big_list, const uint32_t* big_count_dev,
                                  uint32_t max_segments, const unsigned long long* offsets,
-                                 uint32_t* ids, cudaStream_t stream, uint32_t* launches);
+                                 uint32_t* ids, cudaStream_t stream, uint32_t* launches,
+                                 uint32_t longest = 0, void* long_scratch = nullptr, unsigned long long total_ids = 0);
 // coherence pass: order[] = query indices grouped by the Morton cell of the box centre
 // (first 3 axes), cells sized from the batch's own extent; scratch >= reorder_scratch_bytes()
 size_t reorder_scratch_bytes(uint64_t n);

@@ -118,9 +118,10 @@ struct Counters
   unsigned long long total;       // filled by copying offsets[n]
   uint32_t deferred;
   uint32_t big;
-
+  uint32_t max_list;              // longest list that goes to the segment sort
+  uint32_t pad;
 };
-static_assert(sizeof(Counters) == 64, "Counters layout");
+static_assert(sizeof(Counters) == 72, "Counters layout");
 
 enum
 {
@@ -148,7 +149,7 @@ constexpr uint64_t MAX_BATCHES = 1024;                // a call is never cut fin
 struct Slot
 {
   DevBuf d_queries, d_packed, d_order, d_counts, d_offsets, d_ids, d_stash, d_stash_pos, d_deferred, d_big, d_scratch,
-      d_counters, d_cursors;
+      d_counters, d_cursors, d_long;
   HostBuf h_counters;
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
@@ -159,7 +160,7 @@ struct Slot
   void release()
   {
     DevBuf* dev[] = { &d_queries, &d_packed, &d_order, &d_counts, &d_offsets, &d_ids, &d_stash,
-                      &d_stash_pos, &d_deferred, &d_big, &d_scratch, &d_counters, &d_cursors };
+                      &d_stash_pos, &d_deferred, &d_big, &d_scratch, &d_counters, &d_cursors, &d_long };
     for (DevBuf* b : dev)
       b->release();
     h_counters.release();

@@ -6,10 +6,15 @@ namespace rtb
 {
 namespace
 {
-template <int D, int W, bool BOXKEY>
+template <int D, int W, bool BOXKEY, bool COLLECT = false>
 cudaError_t launch_knn_kind(const KnnLaunch& p)
 {
-  auto kernel = knn_traverse_kernel<D, W, BOXKEY>;
+  if constexpr (!COLLECT)
+  {
+    if (p.collect)
+      return launch_knn_kind<D, W, BOXKEY, true>(p);
+  }
+  auto kernel = knn_traverse_kernel<D, W, BOXKEY, COLLECT>;
   const size_t smem = (size_t)(TRAVERSE_THREADS / 32) * 2 * (32u / W + 32u * p.tree.num_levels) * sizeof(uint32_t);
   cudaError_t err = cudaSuccess;
   if (smem > 48 * 1024)

@@ -310,7 +310,7 @@ __device__ void bitonic_ascending(uint32_t* a, uint64_t len)
 __global__ void __launch_bounds__(SORT_THREADS) sort_segments_kernel(const uint32_t* __restrict__ big_list,
                                                                      const uint32_t* __restrict__ big_count,
                                                                      const unsigned long long* __restrict__ offsets,
-                                                                     uint32_t* ids)
+                                                                     uint32_t* ids, uint32_t skip_long)
 {
   __shared__ uint32_t buf[SORT_SMEM_IDS];
   const uint32_t segments = *big_count;
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_segments_kernel(const uint3
         seg[i] = buf[i];
       __syncthreads();
     }
-    else
+    else if (!skip_long)
     {
       __syncthreads();
       bitonic_ascending(seg, len); // in global memory; __syncthreads orders the block's accesses
@@ -338,18 +338,162 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_segments_kernel(const uint3
     }
   }
 }
+
+// ---- lists longer than SORT_SMEM_IDS: one bitonic network over ALL of them at once ------------
+// LongTable = { count, work, then per long list: begin (u64), work_begin (u64), len (u32) } in scratch.
+struct LongSeg
+{
+  unsigned long long begin;      // first id of the list in ids[]
+  unsigned long long work_begin; // exclusive prefix sum of the lengths of the long lists before it
+  unsigned long long len;
+};
+struct LongHeader
+{
+  unsigned int count;            // long lists found
+  unsigned int pad;
+  unsigned long long work;       // sum of their lengths
+};
+
+__global__ void long_init_kernel(LongHeader* h)
+{
+  h->count = 0;
+  h->pad = 0;
+  h->work = 0;
+}
+
+__global__ void __launch_bounds__(256) long_collect_kernel(const uint32_t* __restrict__ big_list,
+                                                           const uint32_t* __restrict__ big_count,
+                                                           const unsigned long long* __restrict__ offsets,
+                                                           LongHeader* h, LongSeg* table, uint32_t capacity)
+{
+  const uint32_t segments = *big_count;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < segments; s += gridDim.x * blockDim.x)
+  {
+    const uint32_t q = big_list[s];
+    const unsigned long long begin = offsets[q];
+    const unsigned long long len = offsets[q + 1] - begin;
+    if (len > SORT_SMEM_IDS)
+    {
+      const unsigned int at = atomicAdd(&h->count, 1u);
+      if (at < capacity)
+      {
+        table[at].begin = begin;
+        table[at].len = len;
+      }
+    }
+  }
+}
+
+// one CTA: work_begin = exclusive scan of len over the table (a few thousand entries at most)
+__global__ void __launch_bounds__(SCAN_THREADS) long_prefix_kernel(LongHeader* h, LongSeg* table, uint32_t capacity)
+{
+  __shared__ unsigned long long warp_sums[32];
+  const unsigned int count = h->count < capacity ? h->count : capacity;
+  unsigned long long carry = 0;
+  for (unsigned int base = 0; base < count; base += SCAN_THREADS)
+  {
+    const unsigned int i = base + threadIdx.x;
+    const unsigned long long v = i < count ? table[i].len : 0ull;
+    unsigned long long total;
+    const unsigned long long inc = block_inclusive(v, warp_sums, &total);
+    if (i < count)
+      table[i].work_begin = carry + inc - v;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+  {
+    h->count = count;
+    h->work = carry;
+  }
+}
+
+// one step (k, j) of the network of bitonic_ascending() over every element of every long list
+__global__ void __launch_bounds__(256) long_step_kernel(const LongHeader* __restrict__ h,
+                                                        const LongSeg* __restrict__ table, uint32_t* ids,
+                                                        unsigned long long k, unsigned long long j)
+{
+  const unsigned int count = h->count;
+  const unsigned long long work = h->work;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < work;
+       e += (unsigned long long)gridDim.x * blockDim.x)
+  {
+    // the list this element belongs to: the last one whose work_begin <= e
+    unsigned int lo = 0, hi = count;
+    while (hi - lo > 1)
+    {
+      const unsigned int mid = (lo + hi) >> 1;
+      if (table[mid].work_begin <= e)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    const unsigned long long len = table[lo].len;
+    const unsigned long long i = e - table[lo].work_begin;
+    const unsigned long long partner = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+    if (partner > i && partner < len)
+    {
+      uint32_t* seg = ids + table[lo].begin;
+      const uint32_t x = seg[i], y = seg[partner];
+      if (x > y)
+      {
+        seg[i] = y;
+        seg[partner] = x;
+      }
+    }
+  }
+}
 } // namespace
+
+// long lists hold more than SORT_SMEM_IDS ids each, so a batch of `total_ids` has at most this many
+static uint32_t long_capacity(unsigned long long total_ids)
+{
+  return (uint32_t)(total_ids / SORT_SMEM_IDS + 1);
+}
+
+size_t long_sort_scratch_bytes(unsigned long long total_ids)
+{
+  return sizeof(LongHeader) + (size_t)long_capacity(total_ids) * sizeof(LongSeg) + 64;
+}
 
 cudaError_t launch_sort_segments(const uint32_t* big_list, const uint32_t* big_count_dev,
                                  uint32_t max_segments, const unsigned long long* offsets,
-                                 uint32_t* ids, cudaStream_t stream, uint32_t* launches)
+                                 uint32_t* ids, cudaStream_t stream, uint32_t* launches, uint32_t longest,
+                                 void* long_scratch, unsigned long long total_ids)
 {
   if (max_segments == 0)
     return cudaSuccess;
+  const bool long_path = longest > SORT_SMEM_IDS && long_scratch != nullptr;
   const unsigned wave = sm_count() * 4u;
   const unsigned grid = max_segments < wave ? max_segments : wave;
-  sort_segments_kernel<<<grid, SORT_THREADS, 0, stream>>>(big_list, big_count_dev, offsets, ids);
+  sort_segments_kernel<<<grid, SORT_THREADS, 0, stream>>>(big_list, big_count_dev, offsets, ids, long_path ? 1u : 0u);
   *launches += 1;
+  if (!long_path)
+    return cudaGetLastError();
+
+  LongHeader* h = static_cast<LongHeader*>(long_scratch);
+  LongSeg* table = reinterpret_cast<LongSeg*>(h + 1);
+  const uint32_t capacity = long_capacity(total_ids);
+  long_init_kernel<<<1, 1, 0, stream>>>(h);
+  const unsigned cgrid = (max_segments + 255) / 256 < wave ? (max_segments + 255) / 256 : wave;
+  long_collect_kernel<<<cgrid, 256, 0, stream>>>(big_list, big_count_dev, offsets, h, table, capacity);
+  long_prefix_kernel<<<1, SCAN_THREADS, 0, stream>>>(h, table, capacity);
+  *launches += 3;
+  // the network of bitonic_ascending(): every comparison ascending, mirror partner on the first step
+  // of a merge, indices beyond a list's length act as +infinity.  `longest` bounds every list, so a
+  // list shorter than the padded size of the longest one simply sees no-op steps at the end.
+  unsigned long long padded = 1;
+  while (padded < longest)
+    padded <<= 1;
+  const unsigned sgrid = sm_count() * 8u;
+  for (unsigned long long k = 2; k <= padded; k <<= 1)
+  {
+    for (unsigned long long j = k >> 1; j > 0; j >>= 1)
+    {
+      long_step_kernel<<<sgrid, 256, 0, stream>>>(h, table, ids, k, j);
+      *launches += 1;
+    }
+  }
   return cudaGetLastError();
 }
 

@@ -471,7 +471,11 @@ box_traverse_kernel(const BoxLaunch p)
       if (PASS == PASS_COUNT || PASS == PASS_COUNT_STATS)
       {
         if (lane == 0)
+        {
           p.counts[qi] = count;
+          if (count > HIT_BUF)
+            atomicMax(p.max_list, count); // the write pass will hand this list to the segment sort
+        }
       }
       else if (PASS == PASS_STASH)
       {
@@ -503,14 +507,20 @@ box_traverse_kernel(const BoxLaunch p)
           slab_pos += count;
           slab_left -= count;
           if (p.sorted && lane == 0)
+          {
             p.big_list[atomicAdd(p.big_count, 1u)] = (uint32_t)qi; // sorted after the gather
+            atomicMax(p.max_list, count);
+          }
         }
         if (lane == 0)
         {
           p.counts[qi] = count;
           p.stash_pos[qi] = where;
           if (where == NO_STASH)
+          {
             p.deferred_list[atomicAdd(p.deferred_count, 1u)] = defer_key;
+            atomicMax(p.max_list, count); // the second traversal writes it, the segment sort orders it
+          }
         }
       }
       else // PASS_WRITE

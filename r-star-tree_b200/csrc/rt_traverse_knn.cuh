@@ -41,7 +41,7 @@ __device__ __forceinline__ void sts_u32x2(uint32_t addr, uint32_t a, uint32_t b)
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 
-template <int D, int W, bool BOXKEY>
+template <int D, int W, bool BOXKEY, bool COLLECT = false> // COLLECT: also count the node visits (RT_COLLECT_VISITS)
 __global__ void __launch_bounds__(TRAVERSE_THREADS)
 knn_traverse_kernel(const KnnLaunch p)
 {
@@ -130,7 +130,7 @@ knn_traverse_kernel(const KnnLaunch p)
         const uint32_t d2b = __float_as_uint(d2);
         const bool valid = link != RT_INVALID_ID;
 
-        if (p.collect)
+        if constexpr (COLLECT)
         {
           visits_leaf += __popc(__ballot_sync(0xFFFFFFFFu, is_leaf && slot == 0 && node != null_link));
           visits_int += __popc(__ballot_sync(0xFFFFFFFFu, !is_leaf && slot == 0));
@@ -200,7 +200,7 @@ knn_traverse_kernel(const KnnLaunch p)
     }
   }
 
-  if (p.collect && lane == 0)
+  if (COLLECT && lane == 0)
   {
     atomicAdd(p.visit_stats + 0, visits_int);
     atomicAdd(p.visit_stats + 1, visits_leaf);

@@ -209,7 +209,11 @@ ray_traverse_kernel(const RayLaunch p)
       if (RMODE == RAY_COUNT)
       {
         if (lane == 0)
+        {
           p.counts[qi] = count;
+          if (count > HIT_BUF)
+            atomicMax(p.max_list, count);
+        }
       }
       else if (RMODE == RAY_WRITE)
       {

@@ -15,13 +15,13 @@ dump() { # object, mangled name, output, title
   } > "$3"
   echo "$3: $(wc -l < "$3") lines"
 }
-dump $L/rt_box_f32.o _ZN3rtb19box_traverse_kernelIfLi3ELi8ELb0ELb0ELj2ELb1EEEvNS_9BoxLaunchE \
+dump $L/rt_box_f32.o _ZN3rtb19box_traverse_kernelIfLi3ELi8ELb0ELb0ELj2ELb1ELb0EEEvNS_9BoxLaunchE \
      profiles/${tag}_box_traverse_f32_3d_w8_stash_quant.sass \
      "rtb::box_traverse_kernel<float, 3, 8, point keys, PASS_STASH, QUANT> -- the headline kernel (BASELINE config 2)"
-dump $L/rt_box_f32.o _ZN3rtb19box_traverse_kernelIfLi8ELi16ELb0ELb0ELj2ELb1EEEvNS_9BoxLaunchE \
+dump $L/rt_box_f32.o _ZN3rtb19box_traverse_kernelIfLi8ELi16ELb0ELb0ELj2ELb1ELb0EEEvNS_9BoxLaunchE \
      profiles/${tag}_box_traverse_f32_8d_w16_stash_quant.sass \
      "rtb::box_traverse_kernel<float, 8, 16, point keys, PASS_STASH, QUANT> -- BASELINE config 4's kernel"
-dump $L/rt_knn.o _ZN3rtb19knn_traverse_kernelILi3ELi8ELb0EEEvNS_9KnnLaunchE \
+dump $L/rt_knn.o _ZN3rtb19knn_traverse_kernelILi3ELi8ELb0ELb0EEEvNS_9KnnLaunchE \
      profiles/${tag}_knn_traverse_3d_w8.sass \
      "rtb::knn_traverse_kernel<3, 8, point keys>"
 dump $L/rt_ray.o _ZN3rtb19ray_traverse_kernelILi8ELb1ELj3EEEvNS_9RayLaunchE \

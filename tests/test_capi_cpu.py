@@ -96,3 +96,25 @@ def test_missing_library_is_an_error_not_a_fallback(rtb, monkeypatch):
     with pytest.raises(rtb.RtError) as err:
         capi.lib()
     assert "no CPU fallback" in str(err.value)
+
+
+def test_batch_planner_never_divides_by_zero_and_covers_the_call(rtb):
+    """the batch planner of pipelined calls (host arithmetic, no device): every plan covers exactly the n
+    queries, tiny or absurd RT_OPT_PIPELINE_BATCH values (the environment override clamps them to 4096
+    instead of refusing them) neither crash nor explode into millions of batches, and the documented
+    ramp B/2, B, 2 B, ~4 B ..., 2 B, B, B/2 comes out for the headline call"""
+    plan = rtb.capi.plan_batches
+    for n in (0, 1, 5, 6, 4095, 4096, 8192, 47003, 1 << 20, 16_000_000, 3_999_999_999):
+        for b in (0, 1, 2, 7, 4095, 4096, 5000, 1 << 20, 1 << 40):
+            sizes = plan(n, b)
+            assert sum(sizes) == n and len(sizes) >= 1
+            assert len(sizes) <= 1100
+            assert all(s > 0 for s in sizes) or n == 0
+            if b == 0:
+                assert sizes == [n]
+    mi = 1 << 20
+    assert plan(16_000_000, mi)[:3] == [mi // 2, mi, 2 * mi] and plan(16_000_000, mi)[-3:] == [2 * mi, mi, mi // 2]
+    assert len(plan(16_000_000, mi)) == 9
+    assert plan(16_000_000, 1) == plan(16_000_000, 4096)          # clamped, not divided by
+    with pytest.raises(rtb.RtError):
+        plan(1 << 32, mi)

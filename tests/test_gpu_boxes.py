@@ -167,6 +167,32 @@ def test_long_hit_lists_take_the_deferred_and_sort_paths(rtb):
         assert csr_equal(tree.query_boxes(q, flags=rtb.RT_COLLECT_VISITS), want)
 
 
+def test_huge_hit_lists_are_sorted_by_the_whole_gpu(rtb):
+    """queries that cover much of a 500 k-point tree (lists of 500 k, ~250 k, ~60 k and ~10 k ids, next
+    to ordinary ones): lists beyond 8192 ids are sorted together by a global-memory network, one launch
+    per step over all their elements, instead of one thread block per list -- still the reference's
+    sorted lists, in single-batch, pipelined and two-pass calls, and in well under a second"""
+    n = 500_000
+    pts = rtb.workloads.uniform_points(n, seed=31)
+    ref = O.RefTree(4).insert(pts)
+    small = rtb.workloads.cube_queries(9000, n, seed=32)
+    big = np.array([[[-1, -1, -1], [2, 2, 2]],
+                    [[0, 0, 0], [0.5, 1, 1]],
+                    [[0.2, 0.2, 0.2], [0.7, 0.7, 0.7]],
+                    [[0.6, 0.1, 0.3], [0.9, 0.4, 0.52]]], np.float32)
+    q = np.concatenate([small[:3000], big[:2], small[3000:6000], big[2:], small[6000:]])
+    want = ref.search_boxes(q)
+    lengths = np.diff(want[0].astype(np.int64))
+    assert lengths.max() == n and (lengths > 8192).sum() == 4
+    with rtb.RTree(4).insert(pts).flatten_device().upload(0) as tree:
+        for batch, flags in ((0, 0), (4096, 0), (0, rtb.RT_COLLECT_VISITS)):
+            tree.set_option(rtb.RT_OPT_PIPELINE_BATCH, batch)
+            got = tree.query_boxes(q, flags=flags)
+            assert csr_equal(got, want)
+            assert tree.stats()["finish_ms"] < 500.0
+            assert tree.stats()["kernel_launches"] > 150       # the steps of the network are launches of their own
+
+
 def test_stash_exhaustion_falls_back_to_the_second_traversal(rtb, monkeypatch):
     n = 30000
     pts = rtb.workloads.uniform_points(n, seed=7)
