@@ -676,7 +676,7 @@ def section_config5(cx, c5):
             "roofline": alg_roofline(alg_per_query * my_n, trav_all,
                                      "per GPU: algorithmic bytes/query counted on the first call x this GPU's queries, "
                                      "over the summed traversal-kernel time of a step",
-                                     "issue (the config-2 kernel on a deeper tree; capture = config 2)", "r2_v3_box_traverse"),
+                                     "issue (the config-2 kernel on a deeper tree; capture = config 2)", "r2_v4_box_traverse"),
             "tree": {"nodes": int(tree.num_nodes), "levels": int(tree.leaf_level) + 1, "blocks_bytes": int(tree.blocks_bytes),
                      "host_build_s": c5.get("build_s"), "flatten_device_s": c5.get("flatten_s"),
                      "broadcast_ms": round(bcast_ms, 3)},
@@ -724,7 +724,7 @@ def section_knn(cx, gpu_tree, ref_tree, points_n):
                    "roofline": alg_roofline(vs["algorithmic_bytes"], trav_all,
                                             "V_int x 224 B + V_leaf x 128 B + 12 B per point in + 8 k out; visits counted "
                                             "by the engine (pruning makes them traversal-order dependent)",
-                                            "issue (instruction issue slots)", "r2_v3_knn_traverse")}
+                                            "issue (instruction issue slots)", "r2_v4_knn_traverse")}
         if cx.want_cpu and ref_tree is not None:
             threads = host_threads()
             oks = []
