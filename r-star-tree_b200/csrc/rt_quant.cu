@@ -69,10 +69,12 @@ __global__ void __launch_bounds__(256) quant_build_kernel(Shape s, const Grid* g
   const uint32_t node = (uint32_t)(tid / s.width), slot = (uint32_t)(tid % s.width);
   if (node > s.num_nodes)
     return;
+  // wide records (8-D): leaf slots are stored packed, see below; their empty form is the same word
+  constexpr bool PACKED_LEAVES = D == 8;
   uint32_t a[D];
 #pragma unroll
   for (int j = 0; j < D; ++j)
-    a[j] = QUANT_GUARD; // an empty slot: a = 0 in every half
+    a[j] = QUANT_GUARD; // an empty slot: a = 0 in every half (a packed leaf slot: s-half 0x8000, never passes)
   uint32_t link = RT_INVALID_ID;
   if (node < s.num_nodes)
   {
@@ -91,6 +93,18 @@ __global__ void __launch_bounds__(256) quant_build_kernel(Shape s, const Grid* g
         hi[d] = leaf ? lo[d] : float_at(block, s.width, words, slot, D + 1 + d);
       }
       quant_slot<D>(lo, hi, grid->lo, grid->scale, a);
+      if (PACKED_LEAVES && leaf)
+      {
+        // a point says the same thing in both halves of its record: keep only s_j = q(p_2j) | q(p_2j+1) << 16
+        // in the first D/2 words (the traversal derives the rest, rt_traverse_box.cuh), zero the others
+#pragma unroll
+        for (int j = 0; j < D / 2; ++j)
+          a[j] = quant(lo[2 * j], grid->lo[2 * j], grid->scale[2 * j])
+                 | (quant(lo[2 * j + 1], grid->lo[2 * j + 1], grid->scale[2 * j + 1]) << 16);
+#pragma unroll
+        for (int j = D / 2; j < D; ++j)
+          a[j] = 0u;
+      }
       link = raw; // leaf entry: the id
       if (!leaf)
       {

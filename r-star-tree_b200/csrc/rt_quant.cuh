@@ -26,6 +26,11 @@
 // bounds to 32767.  In 3-D a node is one 128-byte line instead of two; in 8-D (W = 16) 576 bytes
 // instead of 1088.  A point leaf's quantised block has the stride of its float block (D + 1 words
 // per slot in both), so the float record behind a candidate sits at a constant distance.
+//
+// 8-D leaves are stored PACKED: a point's record would say the same thing in its q-halves and its
+// n-halves, so only s_j = q(p_2j) | q(p_2j+1) << 16 (j < 4) is kept, in the first 16-byte row; the
+// traversal derives G | s_j and 0x00010000 - s_j (= G | n(p) in each half) in registers and never
+// fetches the second row of a leaf (rt_traverse_box.cuh).  An empty leaf slot is s-half 0x8000.
 #pragma once
 
 #include "rt_common.cuh"

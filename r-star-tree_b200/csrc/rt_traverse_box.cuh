@@ -95,14 +95,7 @@ __device__ __forceinline__ void claim_stash_slab(const BoxLaunch& p, int lane, u
 #ifndef RTB_STAGE_TOP
 #define RTB_STAGE_TOP 0
 #endif
-// RTB_PROGRESSIVE_ROWS (experiments on the 8-D kernel, whose quantised records are two 16-byte rows and a
-// link row): 0 = every lane loads the whole record; 1 = row by row, a lane stops fetching once its slot
-// has failed (measured: 16 % SLOWER -- the rows' L2 latencies add up on the step's dependent chain and
-// the skipped sectors do not make up for it); 2 = both rows at once, the link row only for slots that
-// passed.  DESIGN.md section 8 has the numbers.
-#ifndef RTB_PROGRESSIVE_ROWS
-#define RTB_PROGRESSIVE_ROWS 0
-#endif
+
 
 // STRICT (RT_STRICT_OVERLAP, float blocks only): the node filter -- and the key test of box keys under
 // RT_INTERSECTS -- is the reference's N-D geometry_traits<aabb>::is_overlap(aabb, aabb)
@@ -253,47 +246,30 @@ box_traverse_kernel(const BoxLaunch p)
         uint32_t w[QRec::PADDED]; // the slot's quantised record (QUANT)
         if constexpr (QUANT)
         {
-          if constexpr (QRec::NV >= 2 && RTB_PROGRESSIVE_ROWS == 2)
+          if constexpr (D == 8)
           {
-            // wide records: every row at once, but the link row (a ninth wavefront per step) only for
-            // the slots that passed -- one in sixteen
+            // 8-D records are two 16-byte rows + a link row.  A LEAF slot holds a point, whose two
+            // rows would say the same thing twice (q(p) and 32768 - q(p)); the image stores only
+            // s_j = q(p_2j) | q(p_2j+1) << 16 in row 0 (rt_quant.cu) and the second row is derived:
+            // G | s_j and the n-halves = 0x00010000 - s_j (each half 0x10000 - q, no carry for
+            // q >= 1).  More than half of this kernel's node visits are leaves and it is bound by L1
+            // wavefronts, so not fetching their second row is 2 of 4.5 wavefronts per leaf.  An empty
+            // leaf slot is s-half 0x8000: its derived n-half is 0x8000, below every G | n(qhi).
+            static_assert(QRec::NV == 2 && QRec::R == 1, "8-D quantised record: two rows and the link");
             const unsigned char* rec = lane_blocks + (unsigned long long)node * 16u;
-#pragma unroll
-            for (int k = 0; k < QRec::NV; ++k)
-            {
-              const uint4 v = __ldg(reinterpret_cast<const uint4*>(rec + k * W * 16));
-              w[4 * k + 0] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
-            }
+            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rec));
+            uint4 r1 = make_uint4(0u, 0u, 0u, 0u);
+            if (!is_leaf)
+              r1 = __ldg(reinterpret_cast<const uint4*>(rec + W * 16));
+            link = __ldg(reinterpret_cast<const uint32_t*>(rec + 2 * W * 16 - slot * 12));
+            const uint32_t g = is_leaf ? QUANT_GUARD : 0u;
+            w[0] = r0.x | g, w[1] = r0.y | g, w[2] = r0.z | g, w[3] = r0.w | g;
+            w[4] = is_leaf ? 0x00010000u - r0.x : r1.x;
+            w[5] = is_leaf ? 0x00010000u - r0.y : r1.y;
+            w[6] = is_leaf ? 0x00010000u - r0.z : r1.z;
+            w[7] = is_leaf ? 0x00010000u - r0.w : r1.w;
+            w[D] = link;
             hit_bits = quant_pass_bits<D>(w, qb);
-            link = RT_INVALID_ID;
-            if (hit_bits == QUANT_GUARD)
-              link = __ldg(reinterpret_cast<const uint32_t*>(rec + QRec::NV * W * 16 - slot * 12));
-            w[D] = link;
-          }
-          else if constexpr (QRec::NV >= 2 && RTB_PROGRESSIVE_ROWS == 1)
-          {
-            // wide records (8-D: two 16-byte rows + the link): row by row, and a lane whose slot has
-            // already failed fetches no more of it.  Nearly every child of a node is rejected (one in
-            // sixteen passes), mostly by its first row, so the second row and the link row are only
-            // read for the few sectors that hold a surviving slot -- the kernel is bound by the
-            // L2 -> L1 fill of its 576-byte nodes, not by instructions.
-            const unsigned char* rec = lane_blocks + (unsigned long long)node * 16u;
-            hit_bits = QUANT_GUARD;
-#pragma unroll
-            for (int k = 0; k < QRec::NV; ++k)
-            {
-              if (hit_bits == QUANT_GUARD)
-              {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(rec + k * W * 16));
-                w[4 * k + 0] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
-                hit_bits &= (v.x - qb[4 * k + 0]) & (v.y - qb[4 * k + 1]) & (v.z - qb[4 * k + 2]) & (v.w - qb[4 * k + 3]);
-              }
-            }
-            static_assert(QRec::R == 1, "the link is the one-word tail of the record");
-            link = RT_INVALID_ID;
-            if (hit_bits == QUANT_GUARD)
-              link = __ldg(reinterpret_cast<const uint32_t*>(rec + QRec::NV * W * 16 - slot * 12));
-            w[D] = link;
           }
           else
           {
@@ -405,7 +381,11 @@ box_traverse_kernel(const BoxLaunch p)
               // wide records are not kept in registers across the ballots (8 registers = a CTA per SM):
               // the few lanes with a candidate read theirs again, an L1 hit
               uint32_t again[QRec::PADDED];
-              QRec::load(lane_blocks + (unsigned long long)node * 16u, slot, again);
+              const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(lane_blocks + (unsigned long long)node * 16u));
+              again[0] = r0.x | QUANT_GUARD, again[1] = r0.y | QUANT_GUARD;
+              again[2] = r0.z | QUANT_GUARD, again[3] = r0.w | QUANT_GUARD;
+              again[4] = 0x00010000u - r0.x, again[5] = 0x00010000u - r0.y;
+              again[6] = 0x00010000u - r0.z, again[7] = 0x00010000u - r0.w;
               unsure = !quant_strictly_inside<D>(again, qb);
             }
             const uint32_t m_unsure = __ballot_sync(0xFFFFFFFFu, unsure);
