@@ -95,12 +95,9 @@ __global__ void __launch_bounds__(256) quant_build_kernel(Shape s, const Grid* g
       quant_slot<D>(lo, hi, grid->lo, grid->scale, a);
       if (PACKED_LEAVES && leaf)
       {
-        // a point says the same thing in both halves of its record: keep only s_j = q(p_2j) | q(p_2j+1) << 16
-        // in the first D/2 words (the traversal derives the rest, rt_traverse_box.cuh), zero the others
-#pragma unroll
-        for (int j = 0; j < D / 2; ++j)
-          a[j] = quant(lo[2 * j], grid->lo[2 * j], grid->scale[2 * j])
-                 | (quant(lo[2 * j + 1], grid->lo[2 * j + 1], grid->scale[2 * j + 1]) << 16);
+        // a point says the same thing in both halves of its record: keep only the q-words
+        // G | q(p_2j) | q(p_2j+1) << 16 (the first D/2 of quant_slot's words, which is what `a` holds
+        // already); the traversal derives the n-words (rt_traverse_box.cuh), so they are zeroed
 #pragma unroll
         for (int j = D / 2; j < D; ++j)
           a[j] = 0u;

@@ -153,6 +153,10 @@ box_traverse_kernel(const BoxLaunch p)
 
   // this lane's element of a row
   const unsigned char* lane_blocks = opaque((QUANT ? p.tree.qblocks : p.tree.blocks) + slot * 16);
+  // 8-D quantised records: where the lane's link sits behind the two rows (4-byte elements), kept in a
+  // register (ptxas otherwise re-derives it from %tid in every step)
+  uint32_t link_offset = 2 * W * 16 - slot * 12;
+  asm volatile("" : "+r"(link_offset));
   // QUANT: the float record behind a leaf slot, relative to the lane's quantised-image pointer
   const long long leaf_delta = QUANT ? (long long)(p.tree.leaf_blocks - p.tree.qblocks) : 0ll;
   const uint32_t leaf_link_begin = QUANT ? p.tree.qleaf_link_begin : p.tree.leaf_link_begin;
@@ -249,25 +253,28 @@ box_traverse_kernel(const BoxLaunch p)
           if constexpr (D == 8)
           {
             // 8-D records are two 16-byte rows + a link row.  A LEAF slot holds a point, whose two
-            // rows would say the same thing twice (q(p) and 32768 - q(p)); the image stores only
-            // s_j = q(p_2j) | q(p_2j+1) << 16 in row 0 (rt_quant.cu) and the second row is derived:
-            // G | s_j and the n-halves = 0x00010000 - s_j (each half 0x10000 - q, no carry for
-            // q >= 1).  More than half of this kernel's node visits are leaves and it is bound by L1
-            // wavefronts, so not fetching their second row is 2 of 4.5 wavefronts per leaf.  An empty
-            // leaf slot is s-half 0x8000: its derived n-half is 0x8000, below every G | n(qhi).
+            // rows would say the same thing twice (q(p) and 32768 - q(p)); the image stores only the
+            // first, G | q(p_2j) | q(p_2j+1) << 16 (rt_quant.cu), and the second is derived with one
+            // subtraction per word.  More than half of this kernel's node visits are leaves and it is
+            // bound by L1 wavefronts, so not fetching their second row is 2 of 4.5 wavefronts per leaf.
+            // An empty leaf slot is G | 0: its first row already fails every test.
             static_assert(QRec::NV == 2 && QRec::R == 1, "8-D quantised record: two rows and the link");
             const unsigned char* rec = lane_blocks + (unsigned long long)node * 16u;
             const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rec));
-            uint4 r1 = make_uint4(0u, 0u, 0u, 0u);
+            uint4 r1;
             if (!is_leaf)
+            {
               r1 = __ldg(reinterpret_cast<const uint4*>(rec + W * 16));
-            link = __ldg(reinterpret_cast<const uint32_t*>(rec + 2 * W * 16 - slot * 12));
-            const uint32_t g = is_leaf ? QUANT_GUARD : 0u;
-            w[0] = r0.x | g, w[1] = r0.y | g, w[2] = r0.z | g, w[3] = r0.w | g;
-            w[4] = is_leaf ? 0x00010000u - r0.x : r1.x;
-            w[5] = is_leaf ? 0x00010000u - r0.y : r1.y;
-            w[6] = is_leaf ? 0x00010000u - r0.z : r1.z;
-            w[7] = is_leaf ? 0x00010000u - r0.w : r1.w;
+            }
+            else
+            {
+              // each half: 0x18000 - (0x8000 | q) = 0x8000 | (32768 - q); no borrow between the halves
+              r1.x = 0x80018000u - r0.x, r1.y = 0x80018000u - r0.y;
+              r1.z = 0x80018000u - r0.z, r1.w = 0x80018000u - r0.w;
+            }
+            link = __ldg(reinterpret_cast<const uint32_t*>(rec + link_offset));
+            w[0] = r0.x, w[1] = r0.y, w[2] = r0.z, w[3] = r0.w;
+            w[4] = r1.x, w[5] = r1.y, w[6] = r1.z, w[7] = r1.w;
             w[D] = link;
             hit_bits = quant_pass_bits<D>(w, qb);
           }
@@ -382,10 +389,9 @@ box_traverse_kernel(const BoxLaunch p)
               // the few lanes with a candidate read theirs again, an L1 hit
               uint32_t again[QRec::PADDED];
               const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(lane_blocks + (unsigned long long)node * 16u));
-              again[0] = r0.x | QUANT_GUARD, again[1] = r0.y | QUANT_GUARD;
-              again[2] = r0.z | QUANT_GUARD, again[3] = r0.w | QUANT_GUARD;
-              again[4] = 0x00010000u - r0.x, again[5] = 0x00010000u - r0.y;
-              again[6] = 0x00010000u - r0.z, again[7] = 0x00010000u - r0.w;
+              again[0] = r0.x, again[1] = r0.y, again[2] = r0.z, again[3] = r0.w;
+              again[4] = 0x80018000u - r0.x, again[5] = 0x80018000u - r0.y;
+              again[6] = 0x80018000u - r0.z, again[7] = 0x80018000u - r0.w;
               unsure = !quant_strictly_inside<D>(again, qb);
             }
             const uint32_t m_unsure = __ballot_sync(0xFFFFFFFFu, unsure);
