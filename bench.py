@@ -563,7 +563,7 @@ def section_config4(cx, c4):
                                      "SURVEY.md 8d on the float-image visits: V_int x 1088 B + V_leaf x 576 B + 64 B "
                                      "query + 8 + 4 x hits",
                                      "l1-lsu (L1 wavefronts / L2 -> L1 fill of 576-byte quantised nodes)",
-                                     "r2_v3_box_traverse_8d"),
+                                     "r2_v4_box_traverse_8d"),
             "kernel": "rtb::box_traverse_kernel<float,8,16,false,false,PASS_STASH,QUANT>",
             "tree_broadcast_ms": round(bcast_ms, 3), "host_build_s": c4.get("build_s"),
             "parity": parity,
