@@ -4,6 +4,25 @@
 
 #include "rt_common.cuh"
 
+// No __syncwarp() inside the traversal loop (RTB_LOOP_SYNCWARP = 0).  The stack is written and read by
+// different lanes, so the loop needs the lanes of a warp to execute it together -- and they do: the
+// whole warp enters a step converged (the loop condition is a ballot result), the pop is one LDS for
+// all lanes, every step has two full-mask vote.sync between the pop and the push, the push is a
+// predicated STS (no branch), and the only divergent code (the leaf section's `if (lane has a hit)`)
+// sits inside reconvergence barriers (BSSY / BSYNC in the SASS, profiles/r2_*.sass) that close
+// before the next pop.  A converged warp's shared-memory instructions are executed in program order
+// by the LSU, so pop -> push -> pop needs no further barrier; the two explicit ones cost two issue
+// slots per step (3.6 % of the kernel, measured).  RTB_LOOP_SYNCWARP = 1 puts them back (`make
+// variants` builds that as librtree_b200_sync.so for comparison).  The per-query barriers stay.
+#ifndef RTB_LOOP_SYNCWARP
+#define RTB_LOOP_SYNCWARP 0
+#endif
+#if RTB_LOOP_SYNCWARP
+#define RTB_LOOP_SYNC() __syncwarp()
+#else
+#define RTB_LOOP_SYNC() ((void)0)
+#endif
+
 namespace rtb
 {
 

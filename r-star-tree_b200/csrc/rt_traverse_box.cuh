@@ -71,24 +71,7 @@ __device__ __forceinline__ void claim_stash_slab(const BoxLaunch& p, int lane, u
 // (BoxLaunch::packed) -- one 128-bit load per query instead of an index, six floats and six
 // quantisations per warp.
 //
-// No __syncwarp() inside the traversal loop (RTB_LOOP_SYNCWARP = 0).  The stack is written and read by
-// different lanes, so the loop needs the lanes of a warp to execute it together -- and they do: the
-// whole warp enters a step converged (the loop condition is a ballot result), the pop is one LDS for
-// all lanes, every step has two full-mask vote.sync between the pop and the push, the push is a
-// predicated STS (no branch), and the only divergent code (the leaf section's `if (lane has a hit)`)
-// sits inside reconvergence barriers (BSSY / BSYNC in the SASS, profiles/r2_*_loop.sass) that close
-// before the next pop.  A converged warp's shared-memory instructions are executed in program order
-// by the LSU, so pop -> push -> pop needs no further barrier; the two explicit ones cost two issue
-// slots per step (3.6 % of the kernel, measured).  RTB_LOOP_SYNCWARP = 1 puts them back (`make
-// variants` builds that as librtree_b200_sync.so for comparison).  The per-query barriers stay.
-#ifndef RTB_LOOP_SYNCWARP
-#define RTB_LOOP_SYNCWARP 0
-#endif
-#if RTB_LOOP_SYNCWARP
-#define RTB_LOOP_SYNC() __syncwarp()
-#else
-#define RTB_LOOP_SYNC() ((void)0)
-#endif
+// (The traversal loop has no explicit warp barrier: RTB_LOOP_SYNC() in rt_block.cuh says why.)
 // RTB_STAGE_TOP = 1 (experiment, north_star's "top levels staged in shared memory"): every CTA copies
 // the quantised blocks of the top levels (TreeDev::stage_links) into shared memory and reads them
 // from there.  Measured and left off.

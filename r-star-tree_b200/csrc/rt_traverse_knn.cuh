@@ -109,7 +109,7 @@ knn_traverse_kernel(const KnnLaunch p)
         uint32_t node, node_d2;
         lds_u32x2(stack_pop + sp8, node, node_d2);
         sp8 -= min(sp8, (uint32_t)(G * 8));
-        __syncwarp();
+        RTB_LOOP_SYNC();
         if (node_d2 > wd) // the bound has moved past this node since it was pushed
           node = null_link;
 
@@ -187,7 +187,7 @@ knn_traverse_kernel(const KnnLaunch p)
             wi = __shfl_sync(0xFFFFFFFFu, bi, last);
           }
         }
-        __syncwarp();
+        RTB_LOOP_SYNC();
       }
 
       // ---- the k pairs, already ascending by (d2, id) ---------------------------------------------

@@ -126,7 +126,7 @@ ray_traverse_kernel(const RayLaunch p)
         // with fewer than G nodes left the lower groups read the null node (all slots empty)
         const uint32_t node = lds_u32(stack_pop + sp4);
         sp4 -= min(sp4, (uint32_t)(G * 4));
-        __syncwarp();
+        RTB_LOOP_SYNC();
 
         const bool is_leaf = node >= leaf_link_begin;
         uint32_t link;
@@ -203,8 +203,9 @@ ray_traverse_kernel(const RayLaunch p)
             count += __popc(m_leaf);
           }
         }
-        __syncwarp();
+        RTB_LOOP_SYNC();
       }
+      __syncwarp(); // the hit buffer is read across lanes below
 
       if (RMODE == RAY_COUNT)
       {
