@@ -288,11 +288,12 @@ int rt_get_stats(const rt_tree* tree, rt_stats* out);
 /* RT_OPT_TRAVERSE_GRID: CTAs of the persistent traversal kernels; 0 (default) = as many as are
  *   resident at once (SMs x occupancy; one CTA slot per SM is left free in pipelined calls).    */
 #define RT_OPT_TRAVERSE_GRID 4u
-/* RT_OPT_QUANTISED: 1 (default) = box queries on 3-D float32 point-keyed trees with 8-wide blocks
- *   traverse the quantised image rt_upload builds for them (16-byte slot records with conservative
- *   15-bit bounds; leaf candidates are confirmed on the float records, so results are identical);
+/* RT_OPT_QUANTISED: 1 (default) = box queries on float32 point-keyed trees (2-D / 3-D with 8-wide
+ *   blocks, 8-D with 16-wide blocks) traverse the quantised image rt_upload builds for them (slot
+ *   records with conservative 15-bit bounds; a leaf candidate strictly inside the query on the grid is a
+ *   hit, one in a boundary cell is confirmed on its float record, so results are identical);
  *   0 = always the float blocks (the reference's exact filter: what SURVEY.md 8d's visit counts
- *   are defined on).                                                                           */
+ *   are defined on).  Keys with NaN coordinates are outside the contract on either image.        */
 #define RT_OPT_QUANTISED 5u
 int rt_set_option(rt_tree* tree, uint32_t option, uint64_t value);
 /* How rt_query_boxes would cut a host-result call of n queries with RT_OPT_PIPELINE_BATCH =
