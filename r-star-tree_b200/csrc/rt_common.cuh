@@ -1,10 +1,12 @@
 // rt_common.cuh -- shared declarations of the sm_100a query engine (internal header).
 //
 // Division of labour inside librtree_b200.so:
-//   rt_api.cu          C ABI, device buffers, streams / events, the per-call pipeline
+//   rt_api*.cu         the C ABI over rt_handle.cuh (handle, buffers, streams / events): upload / free /
+//                      options (rt_api.cu), the box pipeline (rt_api_boxes.cu), rays, kNN + refit
 //   rt_box_*.cu        instantiations of the box traversal kernel (rt_traverse_box.cuh)
-//   rt_ray.cu          the ray traversal kernels (rt_traverse_ray.cuh)
-//   rt_passes.cu       hand-written scan, gather, segment sort and query reordering
+//   rt_ray.cu, rt_knn.cu   the ray / kNN traversal kernels (rt_traverse_ray.cuh, rt_traverse_knn.cuh)
+//   rt_quant.cu        builds the quantised image; rt_refit.cu refits bounds after keys moved
+//   rt_passes.cu       hand-written scan, gather, segment sort and query reordering / packing
 #pragma once
 
 #include <cstdint>
