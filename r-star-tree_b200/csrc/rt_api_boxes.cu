@@ -483,6 +483,20 @@ int run_box_call(rt_tree* t, BoxCall& c, const void* boxes, uint64_t n, rt_hits*
     s.traverse_steps += b.hc.visits[3];
     s.leaf_lookups += b.hc.lookups;
   }
+  // RTB_TRACE_BATCHES=1: where every batch's phases lie on the call's timeline (ms after the fork),
+  // to stderr -- the tool the batch ramp of plan_batches() was tuned with
+  if (std::getenv("RTB_TRACE_BATCHES") != nullptr)
+  {
+    static const char* const names[EV_COUNT] = { "begin", "h2d", "reorder", "traverse", "counted", "write", "finish", "d2h" };
+    for (size_t k = 0; k < batches.size(); ++k)
+    {
+      std::fprintf(stderr, "[rtb] batch %2zu n %8llu:", k, (unsigned long long)batches[k].n);
+      for (int e = 0; e < EV_COUNT; ++e)
+        std::fprintf(stderr, " %s %.2f", names[e], elapsed(t->ev_fork, batches[k].ev[e]));
+      std::fprintf(stderr, "\n");
+    }
+    std::fprintf(stderr, "[rtb] call: %.2f ms, %zu batches\n", s.total_ms, batches.size());
+  }
   if (c.collect)
   {
     s.visits_internal = v_int;
