@@ -197,9 +197,8 @@ int box_issue_count(rt_tree* t, const BoxCall& c, Batch& b)
   // ---- CSR offsets, then the 64-byte read-back that sizes the id buffer -----------------
   RT_CUDA(rtb::launch_exclusive_scan(s.d_counts.as<uint32_t>(), n, s.d_offsets.as<unsigned long long>(),
                                      s.d_scratch.p, st, &b.launches));
-  RT_CUDA(cudaMemcpyAsync(&dc->total, s.d_offsets.as<unsigned long long>() + n, sizeof(unsigned long long),
-                          cudaMemcpyDeviceToDevice, st));
-  RT_CUDA(cudaMemcpyAsync(s.h_counters.p, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  RT_CUDA(rtb::launch_publish_counters(dc, sizeof(Counters), offsetof(Counters, total),
+                                       s.d_offsets.as<unsigned long long>() + n, s.h_counters.p, st, &b.launches));
   RT_CUDA(cudaEventRecord(b.ev[EV_COUNTED], st));
   return RT_OK;
 }

@@ -119,8 +119,8 @@ int run_rays_pipelined(rt_tree* t, const RayCall& c, uint64_t per_batch, rt_ray_
     RT_CUDA(rtb::launch_ray_kernel(L));
     ++launches;
     RT_CUDA(cudaEventRecord(bev[EV_TRAVERSE], bs));
-    RT_CUDA(cudaMemcpyAsync(t->h_batch_counters.as<Counters>() + k, s.d_counters.p, sizeof(Counters),
-                            cudaMemcpyDeviceToHost, bs));
+    RT_CUDA(rtb::launch_publish_counters(s.d_counters.p, sizeof(Counters), 0, nullptr,
+                                         t->h_batch_counters.as<Counters>() + k, bs, &launches));
     if (c.mode == RT_RAY_CLOSEST)
     {
       RT_CUDA(cudaMemcpyAsync(t->h_ray_t.as<float>() + first, L.t_out, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost,
@@ -243,9 +243,8 @@ int run_all_hits_pipelined(rt_tree* t, const RayCall& c, uint64_t per_batch, rt_
       Counters* dc = s.d_counters.as<Counters>();
       RT_CUDA(rtb::launch_exclusive_scan(s.d_counts.as<uint32_t>(), b.n, s.d_offsets.as<unsigned long long>(),
                                          s.d_scratch.p, bs, &b.launches));
-      RT_CUDA(cudaMemcpyAsync(&dc->total, s.d_offsets.as<unsigned long long>() + b.n, sizeof(unsigned long long),
-                              cudaMemcpyDeviceToDevice, bs));
-      RT_CUDA(cudaMemcpyAsync(s.h_counters.p, dc, sizeof(Counters), cudaMemcpyDeviceToHost, bs));
+      RT_CUDA(rtb::launch_publish_counters(dc, sizeof(Counters), offsetof(Counters, total),
+                                           s.d_offsets.as<unsigned long long>() + b.n, s.h_counters.p, bs, &b.launches));
       RT_CUDA(cudaEventRecord(b.ev[EV_COUNTED], bs));
     }
     if (k < lag)

@@ -196,6 +196,12 @@ cudaError_t launch_refit(unsigned char* blocks, const rt_tree_desc& d, const uin
 size_t scan_scratch_bytes(uint64_t n);
 cudaError_t launch_exclusive_scan(const uint32_t* counts, uint64_t n, unsigned long long* offsets,
                                   void* scratch, cudaStream_t stream, uint32_t* launches);
+// the batch's counter block to mapped pinned host memory by a store from the SM (not through the copy
+// engine, whose queue may hold 100 MB of an earlier batch's result); the 8-byte word at
+// total_offset_bytes is taken from *d_total (offsets[n]) when d_total is not NULL
+cudaError_t launch_publish_counters(const void* d_counters, uint32_t bytes, uint32_t total_offset_bytes,
+                                    const unsigned long long* d_total, void* h_mapped, cudaStream_t stream,
+                                    uint32_t* launches);
 // offsets[0..n) += base (rebases the CSR offsets of one batch of a pipelined call)
 cudaError_t launch_add_base(unsigned long long* offsets, uint64_t n, unsigned long long base,
                             cudaStream_t stream, uint32_t* launches);

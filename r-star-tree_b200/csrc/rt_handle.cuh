@@ -7,6 +7,7 @@
 //   rt_api_knn.cu    rt_query_knn, rt_refit
 #pragma once
 
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -89,7 +90,8 @@ struct HostBuf
     p = nullptr;
     cap = 0;
     const size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMallocHost(&p, want);
+    // (mapped: the counter blocks are written by a store from the SM, launch_publish_counters)
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocMapped);
     if (e != cudaSuccess)
       return e;
     cap = want;

@@ -81,7 +81,10 @@ cudaError_t plan_work(const void* kernel, size_t smem, uint64_t n, int forced_gr
 // ================================ exclusive scan ====================================
 namespace
 {
-constexpr int SCAN_THREADS = 1024;
+// 256-thread CTAs on purpose: in a pipelined call these passes run in the one CTA slot per SM that the
+// persistent traversal kernel of a neighbouring batch leaves free (8 warps); a 1024-thread CTA could not
+// start before that traversal had drained
+constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
@@ -212,6 +215,40 @@ cudaError_t launch_exclusive_scan(const uint32_t* counts, uint64_t n, unsigned l
   scan_tile_offsets<<<1, SCAN_THREADS, 0, stream>>>(tile_sums, tiles);
   scan_write_offsets<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(counts, n, tile_sums, offsets);
   *launches += 3;
+  return cudaGetLastError();
+}
+
+// ================================ counters to the host ==============================
+namespace
+{
+// dst (mapped pinned host memory) = the batch's counter block, with `total` taken from offsets[n].  A
+// store from the SM instead of a 64-byte cudaMemcpy: the copy engine serves copies in order, and a tiny
+// read-back queued behind the previous batch's 100 MB of hit ids held the whole pipeline back.
+__global__ void publish_counters_kernel(const unsigned long long* __restrict__ counters, uint32_t words,
+                                        uint32_t total_word, const unsigned long long* __restrict__ total,
+                                        unsigned long long* dst)
+{
+  const uint32_t i = threadIdx.x;
+  if (i < words)
+    dst[i] = (i == total_word && total != nullptr) ? *total : counters[i];
+  __threadfence_system();
+}
+} // namespace
+
+cudaError_t launch_publish_counters(const void* d_counters, uint32_t bytes, uint32_t total_offset_bytes,
+                                    const unsigned long long* d_total, void* h_mapped, cudaStream_t stream,
+                                    uint32_t* launches)
+{
+  void* d_view = nullptr;
+  cudaError_t err = cudaHostGetDevicePointer(&d_view, h_mapped, 0);
+  if (err != cudaSuccess)
+    return err;
+  if (bytes % 8 != 0 || bytes > 256)
+    return cudaErrorInvalidValue;
+  publish_counters_kernel<<<1, 32, 0, stream>>>(static_cast<const unsigned long long*>(d_counters), bytes / 8,
+                                                total_offset_bytes / 8, d_total,
+                                                static_cast<unsigned long long*>(d_view));
+  *launches += 1;
   return cudaGetLastError();
 }
 
