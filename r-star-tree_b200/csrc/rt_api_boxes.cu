@@ -359,11 +359,51 @@ std::vector<uint64_t> plan_batches(uint64_t n, uint64_t pipeline_batch, bool sin
   return sizes;
 }
 
+// RTB_BATCH_PLAN="a,b,*K,c,d" (a tuning tool, like RTB_TRACE_BATCHES): batches of a, b queries, then what is
+// left over in K equal batches, then c, d.  Ignored unless it is well-formed and adds up to the call
+std::vector<uint64_t> plan_from_env(uint64_t n, const std::vector<uint64_t>& fallback)
+{
+  const char* e = std::getenv("RTB_BATCH_PLAN");
+  if (e == nullptr || fallback.size() < 2)
+    return fallback;
+  std::vector<uint64_t> sizes;
+  uint64_t fixed = 0, split = 0;
+  size_t split_at = 0;
+  while (*e != '\0')
+  {
+    const bool star = *e == '*';
+    char* end = nullptr;
+    const unsigned long long v = std::strtoull(star ? e + 1 : e, &end, 10);
+    if (end == (star ? e + 1 : e) || v == 0 || (star && split != 0))
+      return fallback;
+    if (star)
+      split = v, split_at = sizes.size();
+    else if (v < MIN_PIPELINE_BATCH || v % 4 != 0)
+      return fallback;
+    else
+      sizes.push_back(v), fixed += v;
+    e = *end == ',' ? end + 1 : end;
+    if (*end != ',' && *end != '\0')
+      return fallback;
+  }
+  if (fixed > n || (split == 0 && fixed != n) || (split != 0 && (n - fixed) / split < MIN_PIPELINE_BATCH))
+    return fallback;
+  if (split != 0)
+  {
+    const uint64_t rest = n - fixed, per = ((rest + split - 1) / split + 3) / 4 * 4;
+    std::vector<uint64_t> middle;
+    for (uint64_t done = 0; done < rest; done += per)
+      middle.push_back(rest - done < per ? rest - done : per);
+    sizes.insert(sizes.begin() + (long)split_at, middle.begin(), middle.end());
+  }
+  return sizes.size() <= 4 * MAX_BATCHES ? sizes : fallback;
+}
+
 // everything of a call that touches the device; on failure the caller quiets the handle (abandon_call)
 int run_box_call(rt_tree* t, BoxCall& c, const void* boxes, uint64_t n, rt_hits* out)
 {
   int rc = RT_OK;
-  const std::vector<uint64_t> sizes = plan_batches(n, t->pipeline_batch, c.keep_on_device);
+  const std::vector<uint64_t> sizes = plan_from_env(n, plan_batches(n, t->pipeline_batch, c.keep_on_device));
   const uint64_t n_batches = sizes.size();
   const bool pipelined = n_batches > 1;
   c.pipelined = pipelined;

@@ -6,7 +6,7 @@
 
 // No __syncwarp() inside the traversal loop (RTB_LOOP_SYNCWARP = 0).  The stack is written and read by
 // different lanes, so the loop needs the lanes of a warp to execute it together -- and they do: the
-// whole warp enters a step converged (the loop condition is a ballot result), the pop is one LDS for
+// whole warp enters a step converged (the loop condition is made of ballot results and a warp reduction), the pop is one LDS for
 // all lanes, every step has two full-mask vote.sync between the pop and the push, the push is a
 // predicated STS (no branch), and the only divergent code (the leaf section's `if (lane has a hit)`)
 // sits inside reconvergence barriers (BSSY / BSYNC in the SASS, profiles/r2_*.sass) that close
@@ -21,6 +21,14 @@
 #define RTB_LOOP_SYNC() __syncwarp()
 #else
 #define RTB_LOOP_SYNC() ((void)0)
+#endif
+
+// Whether the wide-record (8-D) box kernel also keeps its stack pointer as a shared address
+// (rt_traverse_box.cuh).  The narrow kernels always do; for the wide one ptxas then moves the pointer
+// into the uniform datapath, which is measured separately (`make variants`: librtree_b200_relwide.so
+// is the build with 0).
+#ifndef RTB_ABS_SP_WIDE
+#define RTB_ABS_SP_WIDE 1
 #endif
 
 namespace rtb

@@ -106,13 +106,20 @@ box_traverse_kernel(const BoxLaunch p)
   // the hit buffer sits at a constant distance below the stack so it needs no register of its own)
   const uint32_t stack_cap = 32u * p.tree.num_levels;
   uint32_t warp_mem = smem_addr(smem + warp * (HIT_BUF + G + stack_cap));
-  asm volatile("" : "+r"(warp_mem)); // likewise: one register for the hit buffer, the stack and the null words
+  // one register for the hit buffer, the stack and the null words
+  constexpr bool ABS_SP = D <= 3 || RTB_ABS_SP_WIDE; // see the stack pointer in the query loop
+  if constexpr (ABS_SP)
+    warp_mem = __reduce_min_sync(0xFFFFFFFFu, warp_mem); // a warp reduction: ptxas then knows it to be warp-uniform
+  else
+    asm volatile("" : "+r"(warp_mem));
   const uint32_t stack = warp_mem + (HIT_BUF + G) * 4u;
   constexpr uint32_t HITBUF_BELOW = (HIT_BUF + G) * 4u; // hit buffer = stack - HITBUF_BELOW
-  // group g pops the word at stack_pop + 4 * sp, i.e. stack index sp - G + g: with fewer than G
+  // group g pops the word at stack index sp - G + g: with fewer than G
   // nodes left the lower groups read the null node below the stack (a block of empty slots),
   // so popping needs no "is this group active" logic at all
-  const uint32_t stack_pop = stack + (grp - G) * 4u;
+  // (an offset from the stack pointer; see the query loop for what that is counted from)
+  const uint32_t sp_base = ABS_SP ? warp_mem : 0u;
+  const uint32_t pop_offset = warp_mem - sp_base + HITBUF_BELOW + (grp - G) * 4u;
   const uint32_t null_link = QUANT ? p.tree.qnull_link : p.tree.null_link;
   if (lane < G)
     sts_u32(stack - G * 4u + lane * 4u, null_link);
@@ -214,15 +221,22 @@ box_traverse_kernel(const BoxLaunch p)
       if (PASS == PASS_STASH && slab_left < max(HIT_BUF, p.stash_slab / 4))
         claim_stash_slab(p, lane, slab_pos, slab_left);
       uint32_t count = 0;
-      uint32_t sp4 = 4u; // bytes on the stack (kept warp-uniform: it only ever sees ballots)
+      // the stack pointer = sp_base + the bytes on the stack (warp-uniform: it only ever sees ballots and
+      // warp_mem).  Narrow records count it from the warp's shared memory, i.e. keep it as an address, so
+      // that neither the pop nor the push has to add the warp's base: two instructions per step
+      // (profiles/r2_box_traverse_f32_3d_w8_stash_quant.sass).  For the wide (8-D) kernel see RTB_ABS_SP_WIDE
+      uint32_t spw = sp_base + 4u;
       if (lane == 0)
         sts_u32(stack, 0u); // the root; its own bound is never tested (reference rtree.hpp:984)
       __syncwarp();
 
-      while (sp4 != 0)
+      while (spw != sp_base)
       {
-        const uint32_t node = lds_u32(stack_pop + sp4);
-        sp4 -= min(sp4, (uint32_t)(G * 4));
+        const uint32_t node = lds_u32(spw + pop_offset);
+        if constexpr (ABS_SP)
+          spw = max(spw - (uint32_t)(G * 4), sp_base); // (shared addresses of dynamic memory are >= 1024: no wrap)
+        else
+          spw -= min(spw, (uint32_t)(G * 4));
         RTB_LOOP_SYNC();
 
         const bool is_leaf = node >= leaf_link_begin;
@@ -308,7 +322,7 @@ box_traverse_kernel(const BoxLaunch p)
           }
         }
 
-        uint32_t m_leaf, m_int;
+        uint32_t m_leaf, m_int, spw_next;
         if constexpr (QUANT && PASS != PASS_COUNT_STATS)
         {
           // the two ballots and the push, spelled out: three compares for (leaf?, hit && leaf, hit &&
@@ -325,14 +339,15 @@ box_traverse_kernel(const BoxLaunch p)
                        "and.b32 t, %1, %6;\n\t"
                        "popc.b32 t, t;\n\t"
                        "mad.lo.u32 t, t, 4, %7;\n\t"
-                       "@pint st.shared.u32 [t+%10], %8;\n\t"
+                       "@pint st.shared.u32 [t+%9], %8;\n\t"
                        "popc.b32 t, %1;\n\t"
-                       "mad.lo.u32 %2, t, 4, %9;\n\t"
+                       "mad.lo.u32 %2, t, 4, %10;\n\t"
                        "}"
-                       : "=r"(m_leaf), "=r"(m_int), "=r"(sp4)
-                       : "r"(node), "r"(leaf_link_begin), "r"(hit_bits), "r"(lt_mask), "r"(warp_mem + sp4), "r"(link),
-                         "r"(sp4), "n"(HITBUF_BELOW)
+                       : "=r"(m_leaf), "=r"(m_int), "=r"(spw_next)
+                       : "r"(node), "r"(leaf_link_begin), "r"(hit_bits), "r"(lt_mask), "r"(spw + (warp_mem - sp_base)),
+                         "r"(link), "n"(HITBUF_BELOW), "r"(spw)
                        : "memory");
+          spw = spw_next;
         }
         else
         {
@@ -348,25 +363,55 @@ box_traverse_kernel(const BoxLaunch p)
 
           // children to descend: compact onto the stack in lane order (keeps it level-sorted)
           if (hit && !is_leaf)
-            sts_u32(stack + sp4 + __popc(m_int & lt_mask) * 4u, link);
-          sp4 += __popc(m_int) * 4u;
+            sts_u32(spw + (warp_mem - sp_base) + HITBUF_BELOW + __popc(m_int & lt_mask) * 4u, link);
+          spw += __popc(m_int) * 4u;
         }
 
         // leaf entries that satisfy the predicate
         if (m_leaf != 0)
         {
-          uint32_t m_hits = m_leaf;
-          bool leaf_hit = hit && is_leaf;
+          // the lanes in `m_hits` (this one iff `leaf_hit`) hold a hit: into the hit buffer / slab / list
+          auto record_hits = [&](const bool leaf_hit, const uint32_t m_hits)
+          {
+            if (PASS == PASS_STASH || PASS == PASS_WRITE)
+            {
+              if (leaf_hit)
+              {
+                const uint32_t at = count + __popc(m_hits & lt_mask);
+                if (buffered)
+                {
+                  if (at < HIT_BUF)
+                    sts_u32(warp_mem + at * 4u, link);
+                  else if (PASS == PASS_STASH && at < slab_left)
+                    p.stash[slab_pos + at] = link; // beyond the hit buffer: straight into the warp's slab,
+                                                   // at its final place there (sorted after the gather)
+                }
+                else if (PASS == PASS_WRITE && at < expect)
+                {
+                  p.ids[out_base + at] = link;
+                }
+              }
+            }
+            count += __popc(m_hits);
+            if (PASS == PASS_COUNT && p.stop_at_first && count != 0)
+            {
+              // the functor-returns-true abort of reference rtree.hpp:994-997: which hit came first
+              // depends on the traversal order, "there is one" does not
+              count = 1;
+              spw = sp_base;
+            }
+          };
           if constexpr (QUANT)
           {
             // a candidate strictly inside the query on the grid is a hit; one in a boundary cell of
             // the query gets the reference's exact test on its float record
+            const bool candidate = hit && is_leaf;
             bool unsure = false;
             if constexpr (D <= 3)
             {
-              unsure = leaf_hit && !quant_strictly_inside<D>(w, qb);
+              unsure = candidate && !quant_strictly_inside<D>(w, qb);
             }
-            else if (leaf_hit)
+            else if (candidate)
             {
               // wide records are not kept in registers across the ballots (8 registers = a CTA per SM):
               // the few lanes with a candidate read theirs again, an L1 hit
@@ -378,8 +423,15 @@ box_traverse_kernel(const BoxLaunch p)
               unsure = !quant_strictly_inside<D>(again, qb);
             }
             const uint32_t m_unsure = __ballot_sync(0xFFFFFFFFu, unsure);
-            if (m_unsure != 0)
+            if (m_unsure == 0)
             {
+              // the common case gets its own copy of the bookkeeping, so that "this lane holds a hit"
+              // stays a predicate instead of travelling through a register to the join
+              record_hits(candidate, m_leaf);
+            }
+            else
+            {
+              bool leaf_hit = candidate;
               if (unsure)
               {
                 // the float block of a point leaf has the stride of its quantised block
@@ -399,37 +451,14 @@ box_traverse_kernel(const BoxLaunch p)
                 }
                 leaf_hit = inside;
               }
-              m_hits = __ballot_sync(0xFFFFFFFFu, leaf_hit);
               if (PASS == PASS_COUNT_STATS)
                 lookups += __popc(m_unsure);
+              record_hits(leaf_hit, __ballot_sync(0xFFFFFFFFu, leaf_hit));
             }
           }
-          if (PASS == PASS_STASH || PASS == PASS_WRITE)
+          else
           {
-            if (leaf_hit)
-            {
-              const uint32_t at = count + __popc(m_hits & lt_mask);
-              if (buffered)
-              {
-                if (at < HIT_BUF)
-                  sts_u32(warp_mem + at * 4u, link);
-                else if (PASS == PASS_STASH && at < slab_left)
-                  p.stash[slab_pos + at] = link; // beyond the hit buffer: straight into the warp's slab,
-                                                 // at its final place there (sorted after the gather)
-              }
-              else if (PASS == PASS_WRITE && at < expect)
-              {
-                p.ids[out_base + at] = link;
-              }
-            }
-          }
-          count += __popc(m_hits);
-          if (PASS == PASS_COUNT && p.stop_at_first && count != 0)
-          {
-            // the functor-returns-true abort of reference rtree.hpp:994-997: which hit came first
-            // depends on the traversal order, "there is one" does not
-            count = 1;
-            sp4 = 0;
+            record_hits(hit && is_leaf, m_leaf);
           }
         }
         RTB_LOOP_SYNC();

@@ -16,14 +16,32 @@ else:
     image.save(path)
 tree = image.upload(0)
 hq = torch.from_numpy(W.cube_queries(Q, N, seed=43)).pin_memory()
-for batch in [int(x) for x in os.environ.get("SWEEP", "1048576").split(",")]:
-    tree.set_option(capi.RT_OPT_PIPELINE_BATCH, batch)
+def timed_calls(label, trace_last=True):
+    best = 1e9
     for i in range(4):
-        if i == 3:
+        if i == 3 and trace_last:
             os.environ["RTB_TRACE_BATCHES"] = "1"
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         out = tree.query_boxes_raw(hq.data_ptr(), Q, capi.RT_POINT_IN_BOX, 0)
         wall = (time.perf_counter() - t0) * 1e3
         os.environ.pop("RTB_TRACE_BATCHES", None)
-        print("batch %d call %d: wall %.2f ms, engine %.2f ms" % (batch, i, wall, tree.stats()["total_ms"]), flush=True)
+        engine = tree.stats()["total_ms"]
+        best = min(best, engine) if i else best
+        print("%s call %d: wall %.2f ms, engine %.2f ms" % (label, i, wall, engine), flush=True)
+    return best
+
+# PLANS: ';'-separated RTB_BATCH_PLAN strings (sizes in units of 1024 queries), each timed like a SWEEP entry
+if os.environ.get("PLANS"):
+    results = []
+    for plan in os.environ["PLANS"].split(";"):
+        os.environ["RTB_BATCH_PLAN"] = ",".join(x if x.startswith("*") else str(int(float(x) * 1024)) for x in plan.split(","))
+        results.append((timed_calls("plan " + plan, trace_last=os.environ.get("TRACE_PLANS") == "1"), plan))
+    os.environ.pop("RTB_BATCH_PLAN", None)
+    results.append((timed_calls("default plan", trace_last=False), "default"))
+    for ms, plan in sorted(results):
+        print("best of 3: %.2f ms  %s" % (ms, plan))
+    sys.exit(0)
+for batch in [int(x) for x in os.environ.get("SWEEP", "1048576").split(",")]:
+    tree.set_option(capi.RT_OPT_PIPELINE_BATCH, batch)
+    timed_calls("batch %d" % batch)
