@@ -269,7 +269,17 @@ box_traverse_kernel(const BoxLaunch p)
               r1.x = 0x80018000u - r0.x, r1.y = 0x80018000u - r0.y;
               r1.z = 0x80018000u - r0.z, r1.w = 0x80018000u - r0.w;
             }
-            link = __ldg(reinterpret_cast<const uint32_t*>(rec + link_offset));
+            // (a leaf slot's link is the point's id: only a hit needs it, and the leaf section fetches it then --
+            // 13 hits in the 29,000 leaf slots a config-4 query looks at)
+            // (a predicated load that leaves the register alone otherwise: nothing reads a leaf lane's `link`
+            // before the leaf section has set it)
+            asm volatile("{\n\t"
+                         ".reg .pred p;\n\t"
+                         "setp.lt.u32 p, %1, %2;\n\t"
+                         "@p ld.global.nc.u32 %0, [%3];\n\t"
+                         "}"
+                         : "=r"(link)
+                         : "r"(node), "r"(leaf_link_begin), "l"(rec + link_offset));
             w[0] = r0.x, w[1] = r0.y, w[2] = r0.z, w[3] = r0.w;
             w[4] = r1.x, w[5] = r1.y, w[6] = r1.z, w[7] = r1.w;
             w[D] = link;
@@ -416,7 +426,9 @@ box_traverse_kernel(const BoxLaunch p)
               // wide records are not kept in registers across the ballots (8 registers = a CTA per SM):
               // the few lanes with a candidate read theirs again, an L1 hit
               uint32_t again[QRec::PADDED];
-              const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(lane_blocks + (unsigned long long)node * 16u));
+              const unsigned char* rec = lane_blocks + (unsigned long long)node * 16u;
+              const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rec));
+              link = __ldg(reinterpret_cast<const uint32_t*>(rec + link_offset));
               again[0] = r0.x, again[1] = r0.y, again[2] = r0.z, again[3] = r0.w;
               again[4] = 0x80018000u - r0.x, again[5] = 0x80018000u - r0.y;
               again[6] = 0x80018000u - r0.z, again[7] = 0x80018000u - r0.w;
