@@ -147,7 +147,6 @@ box_traverse_kernel(const BoxLaunch p)
   // register (ptxas otherwise re-derives it from %tid in every step)
   uint32_t link_offset = 2 * W * 16 - slot * 12;
   asm volatile("" : "+r"(link_offset));
-  const unsigned char* lane_links = opaque(lane_blocks + link_offset);
   // QUANT: the float record behind a leaf slot, relative to the lane's quantised-image pointer
   const long long leaf_delta = QUANT ? (long long)(p.tree.leaf_blocks - p.tree.qblocks) : 0ll;
   const uint32_t leaf_link_begin = QUANT ? p.tree.qleaf_link_begin : p.tree.leaf_link_begin;
@@ -276,11 +275,11 @@ box_traverse_kernel(const BoxLaunch p)
             // before the leaf section has set it)
             asm volatile("{\n\t"
                          ".reg .pred p;\n\t"
-                         "setp.ge.u32 p, %1, %2;\n\t" // (spelled like the compiler's own `is_leaf`: ptxas merges them)
-                         "@!p ld.global.nc.u32 %0, [%3];\n\t"
+                         "setp.lt.u32 p, %1, %2;\n\t"
+                         "@p ld.global.nc.u32 %0, [%3];\n\t"
                          "}"
                          : "=r"(link)
-                         : "r"(node), "r"(leaf_link_begin), "l"(lane_links + (unsigned long long)node * 16u));
+                         : "r"(node), "r"(leaf_link_begin), "l"(rec + link_offset));
             w[0] = r0.x, w[1] = r0.y, w[2] = r0.z, w[3] = r0.w;
             w[4] = r1.x, w[5] = r1.y, w[6] = r1.z, w[7] = r1.w;
             w[D] = link;
