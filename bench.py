@@ -563,7 +563,7 @@ def section_config4(cx, c4):
                                      "SURVEY.md 8d on the float-image visits: V_int x 1088 B + V_leaf x 576 B + 64 B "
                                      "query + 8 + 4 x hits",
                                      "l1-lsu (L1 wavefronts / L2 -> L1 fill of 576-byte quantised nodes)",
-                                     "r2_v4_box_traverse_8d"),
+                                     "r2_v6_box_traverse_8d"),
             "kernel": "rtb::box_traverse_kernel<float,8,16,false,false,PASS_STASH,QUANT>",
             "tree_broadcast_ms": round(bcast_ms, 3), "host_build_s": c4.get("build_s"),
             "parity": parity,
@@ -676,7 +676,7 @@ def section_config5(cx, c5):
             "roofline": alg_roofline(alg_per_query * my_n, trav_all,
                                      "per GPU: algorithmic bytes/query counted on the first call x this GPU's queries, "
                                      "over the summed traversal-kernel time of a step",
-                                     "issue (the config-2 kernel on a deeper tree; capture = config 2)", "r2_v4_box_traverse"),
+                                     "issue (the config-2 kernel on a deeper tree; capture = config 2)", "r2_v6_box_traverse"),
             "tree": {"nodes": int(tree.num_nodes), "levels": int(tree.leaf_level) + 1, "blocks_bytes": int(tree.blocks_bytes),
                      "host_build_s": c5.get("build_s"), "flatten_device_s": c5.get("flatten_s"),
                      "broadcast_ms": round(bcast_ms, 3)},
