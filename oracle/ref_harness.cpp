@@ -80,6 +80,7 @@ struct ITree
   virtual ~ITree() {}
   virtual void insert(const void* keys, uint64_t n, uint32_t first_id) = 0;
   virtual int64_t set_keys(const void* keys, uint64_t n) = 0;
+  virtual uint64_t erase_ids(const uint32_t* ids, uint64_t n) = 0;
   virtual uint32_t leaf_level() const = 0;
   virtual uint64_t size() const = 0;
   virtual void rebalance() = 0;
@@ -178,6 +179,26 @@ struct TreeImpl : ITree
       tree.rebound(it);
     have_flat = false;
     return (int64_t)i;
+  }
+  // the reference's own RTree::erase(iterator) (include/RTree/rtree.hpp:372-457) on the first value
+  // whose mapped id matches, one id after the other in the order given
+  uint64_t erase_ids(const uint32_t* ids, uint64_t n) override
+  {
+    uint64_t erased = 0;
+    for (uint64_t i = 0; i < n; ++i)
+    {
+      for (auto it = tree.begin(); it != tree.end(); ++it)
+      {
+        if (it->second == ids[i])
+        {
+          tree.erase(it);
+          ++erased;
+          break;
+        }
+      }
+    }
+    have_flat = false;
+    return erased;
   }
   uint32_t leaf_level() const override { return (uint32_t)tree.leaf_level(); }
   uint64_t size() const override { return tree.size(); }
@@ -636,6 +657,10 @@ extern "C"
   int64_t ref_tree_set_keys(void* h, const void* keys, uint64_t n)
   {
     return static_cast<ITree*>(h)->set_keys(keys, n);
+  }
+  uint64_t ref_tree_erase_ids(void* h, const uint32_t* ids, uint64_t n)
+  {
+    return static_cast<ITree*>(h)->erase_ids(ids, n);
   }
   int64_t ref_search_knn(void* h, const float* points, uint64_t n, uint32_t k, int threads,
                          uint32_t* ids_out, float* d2_out, double* seconds)

@@ -82,6 +82,8 @@ def ref_lib():
                                         C.POINTER(C.c_double)]
         lib.ref_tree_set_keys.restype = C.c_int64
         lib.ref_tree_set_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.ref_tree_erase_ids.restype = C.c_uint64
+        lib.ref_tree_erase_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         lib.ref_search_knn.restype = C.c_int64
         lib.ref_search_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int,
                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
@@ -201,6 +203,12 @@ class RefTree:
         got = self.lib.ref_tree_set_keys(self.h, _ptr(keys), keys.size // per)
         assert got == keys.size // per, "set_keys: key count differs from the tree's size"
         return self
+
+    def erase_ids(self, ids):
+        """the reference's erase(iterator) (include/RTree/rtree.hpp:372-457) on the value holding each id,
+        in the order given; returns how many were found"""
+        ids = np.ascontiguousarray(ids, np.uint32)
+        return int(self.lib.ref_tree_erase_ids(self.h, _ptr(ids), ids.size))
 
     def leaf_level(self):
         return self.lib.ref_tree_leaf_level(self.h)

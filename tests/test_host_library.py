@@ -100,6 +100,42 @@ def test_erase_clear_rebalance(rtb):
     assert len(flat["nodes"]) == 1 and flat["nodes"][0, 1] == 0
 
 
+def _same_flat(mine, ref):
+    return (mine["leaf_level"] == ref.leaf_level and np.array_equal(mine["nodes"], ref.nodes)
+            and np.array_equal(mine["children"], ref.children) and np.array_equal(mine["data"], ref.data)
+            and np.array_equal(mine["children_bound"].view(np.uint8), ref.bounds.view(np.uint8)))
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", sorted(O.KINDS))
+def test_erase_gives_the_reference_tree(rtb, kind):
+    """erase(iterator) against the reference's own (include/RTree/rtree.hpp:372-457): after every batch of
+    deletions -- under-full nodes dissolved, their content re-inserted, the root collapsed -- flatten() is
+    bit-identical, down to the empty tree; then the same for inserts into the thinned tree and rebalance()"""
+    n = 900
+    keys = make_keys(kind, n, 200 + kind)
+    mine, ref = rtb.RTree(kind).insert(keys), O.RefTree(kind).insert(keys)
+    order = np.random.default_rng(kind).permutation(n).astype(np.uint32)
+    for start in range(0, 600, 150):
+        batch = order[start:start + 150]
+        assert mine.erase_ids(batch) == ref.erase_ids(batch) == len(batch)
+        assert _same_flat(mine.flatten(), ref.flatten())
+    # values go back into the thinned tree (ids beyond the first batch's)
+    more = make_keys(kind, 200, 300 + kind)
+    mine.insert(more, first_id=n)
+    ref.insert(more, first_id=n)
+    assert _same_flat(mine.flatten(), ref.flatten())
+    mine.rebalance()
+    ref.rebalance()
+    assert _same_flat(mine.flatten(), ref.flatten())
+    # an id that is not there is not an error, and the rest goes down to the empty tree
+    assert mine.erase_ids(order[:5]) == ref.erase_ids(order[:5]) == 0
+    rest = np.concatenate([order[600:], np.arange(n, n + 200, dtype=np.uint32)])
+    assert mine.erase_ids(rest) == ref.erase_ids(rest) == len(rest)
+    assert mine.size() == ref.size() == 0
+    assert _same_flat(mine.flatten(), ref.flatten())
+
+
 @pytest.mark.parametrize("kind", [0, 2, 4, 5, 6])
 def test_flatten_device_layout(rtb, kind):
     """level-ordered SoA blocks: every node's entries are those of flatten(), in slot order,
