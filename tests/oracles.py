@@ -82,8 +82,9 @@ def ref_lib():
                                         C.POINTER(C.c_double)]
         lib.ref_tree_set_keys.restype = C.c_int64
         lib.ref_tree_set_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
-        lib.ref_tree_erase_ids.restype = C.c_uint64
-        lib.ref_tree_erase_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        if hasattr(lib, "ref_tree_erase_ids"):  # (a prebuilt _ref from before the symbol existed still serves the rest)
+            lib.ref_tree_erase_ids.restype = C.c_uint64
+            lib.ref_tree_erase_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         lib.ref_search_knn.restype = C.c_int64
         lib.ref_search_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int,
                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
