@@ -1,0 +1,80 @@
+"""The reference's OWN unit tests and example programs, compiled where they lie under /root/reference (never
+copied) against the host library of this repo: the drop-in claim of INTEGRATION.md section A, checked with the
+reference's own code.
+
+* /root/reference/test/rtree.cpp (Insert, Erase, Assign, Clear, MoveOnlyValue, StaticVector, Flatten -- the
+  last one is the known-answer test of the flat form) builds against r-star-tree_b200/include and
+  passes.  GoogleTest is not in this image; tests/shim/gtest/gtest.h stands in for it, and the same shim is
+  validated on the reference's own headers first.
+* example/sample/sample.cpp and example/visualize_{1d,2d,3d}/main.cpp print the tree they built (bounds of every
+  node, level by level); with std::random_device pinned (tests/shim/fixed_random_device.h) the output under our
+  headers is byte-identical to the output under the reference's.
+
+CPU only; skipped where the reference sources are absent (the GPU box)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+SHIM = os.path.join(ROOT, "tests", "shim")
+OURS = ["-I" + os.path.join(ROOT, "r-star-tree_b200", "include"), "-I" + os.path.join(ROOT, "include")]
+THEIRS = ["-I" + os.path.join(REF, "include")]
+CXX = shutil.which("g++")
+
+pytestmark = pytest.mark.skipif(CXX is None or not os.path.isdir(os.path.join(REF, "test")),
+                                reason="reference sources (or g++) not present")
+
+EXAMPLES = {
+    "sample": ("example/sample/sample.cpp", [[]]),
+    "visualize_1d": ("example/visualize_1d/main.cpp", [["37"], ["1000"]]),
+    "visualize_2d": ("example/visualize_2d/main.cpp", [["37"], ["1000"]]),
+    "visualize_3d": ("example/visualize_3d/main.cpp", [["37"], ["1000"]]),
+}
+
+
+def _compile_all(jobs):
+    """jobs: {output path: argument list}; all compilers run side by side"""
+    procs = {out: subprocess.Popen([CXX, "-std=c++17", "-O1", "-w"] + args + ["-o", out],
+                                   stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for out, args in jobs.items()}
+    for out, p in procs.items():
+        log, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, "compiling %s failed:\n%s" % (os.path.basename(out), log[-4000:])
+
+
+@pytest.fixture(scope="module")
+def built(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("reference_programs"))
+    unit = [os.path.join(REF, "test", "rtree.cpp"), os.path.join(REF, "test", "main.cpp"), "-I" + SHIM]
+    jobs = {os.path.join(d, "unit_ours"): unit + OURS, os.path.join(d, "unit_theirs"): unit + THEIRS}
+    pin = ["-include", os.path.join(SHIM, "fixed_random_device.h")]
+    for name, (src, _) in EXAMPLES.items():
+        jobs[os.path.join(d, name + "_ours")] = pin + [os.path.join(REF, src)] + OURS
+        jobs[os.path.join(d, name + "_theirs")] = pin + [os.path.join(REF, src)] + THEIRS
+    _compile_all(jobs)
+    return d
+
+
+@pytest.mark.parametrize("headers", ["theirs", "ours"])
+def test_reference_unit_tests_pass(built, headers):
+    """`theirs` validates the gtest shim; `ours` is the claim"""
+    r = subprocess.run([os.path.join(built, "unit_" + headers)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "7 tests ran, 0 failed" in r.stdout
+    for name in ("Insert", "Erase", "Assign", "Clear", "MoveOnlyValue", "StaticVector", "Flatten"):
+        assert "[       OK ] RTreeTest.%s" % name in r.stdout
+
+
+@pytest.mark.parametrize("name", sorted(EXAMPLES))
+def test_reference_examples_print_the_same_tree(built, name):
+    for args in EXAMPLES[name][1]:
+        out = {}
+        for headers in ("theirs", "ours"):
+            r = subprocess.run([os.path.join(built, "%s_%s" % (name, headers))] + args, capture_output=True, timeout=600)
+            assert r.returncode == 0
+            out[headers] = r.stdout
+        assert len(out["theirs"]) > 50
+        assert out["ours"] == out["theirs"], "%s %s: output differs from the reference's" % (name, args)
