@@ -10,6 +10,13 @@ reference's own code.
   node, level by level); with std::random_device pinned (tests/shim/fixed_random_device.h) the output under our
   headers is byte-identical to the output under the reference's.
 
+* example/eigen/main.cpp (a user vector type bound through geometry_traits) builds and runs against both, with
+  tests/shim/Eigen/Core standing in for Eigen.
+* tests/cpp/api_surface.cpp (ours) drives the whole documented API -- user geometry + geometry_traits, a user
+  Config with QuadraticSplit, tri-state filter and aborting functor, iterators, node pointers, rebound /
+  rebalance, erase, copy / move, flatten -- and prints digests (tree shape, traversal order, filter-call counts);
+  the output under our headers equals the output under the reference's byte for byte.
+
 CPU only; skipped where the reference sources are absent (the GPU box)."""
 import os
 import shutil
@@ -54,6 +61,12 @@ def built(tmp_path_factory):
     for name, (src, _) in EXAMPLES.items():
         jobs[os.path.join(d, name + "_ours")] = pin + [os.path.join(REF, src)] + OURS
         jobs[os.path.join(d, name + "_theirs")] = pin + [os.path.join(REF, src)] + THEIRS
+    eigen = [os.path.join(REF, "example", "eigen", "main.cpp"), "-I" + SHIM]
+    jobs[os.path.join(d, "eigen_ours")] = eigen + OURS
+    jobs[os.path.join(d, "eigen_theirs")] = eigen + THEIRS
+    api = [os.path.join(ROOT, "tests", "cpp", "api_surface.cpp")]
+    jobs[os.path.join(d, "api_ours")] = api + ["-DRTB_ONLY_OURS"] + OURS
+    jobs[os.path.join(d, "api_theirs")] = api + THEIRS
     _compile_all(jobs)
     return d
 
@@ -78,3 +91,25 @@ def test_reference_examples_print_the_same_tree(built, name):
             out[headers] = r.stdout
         assert len(out["theirs"]) > 50
         assert out["ours"] == out["theirs"], "%s %s: output differs from the reference's" % (name, args)
+
+
+def test_reference_eigen_example_builds_with_user_traits(built):
+    for headers in ("theirs", "ours"):
+        assert subprocess.run([os.path.join(built, "eigen_" + headers)], timeout=60).returncode == 0
+
+
+def test_documented_api_behaves_like_the_reference(built):
+    out = {}
+    for headers in ("theirs", "ours"):
+        r = subprocess.run([os.path.join(built, "api_" + headers)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[headers] = r.stdout.splitlines()
+    extra = [line for line in out["ours"] if line.startswith("ours:")]
+    assert [line for line in out["ours"] if not line.startswith("ours:")] == out["theirs"]
+    assert len(out["theirs"]) > 40 and "copies equal the original: 1" in "\n".join(out["theirs"])
+    # the members only our headers can instantiate agree with the portable calls next to them
+    assert len(extra) == 2
+    for line in extra:
+        words = line.replace("(", " ").replace(")", " ").replace(";", " ").split()
+        assert words[3] == words[6], line            # search_iterator saw every value
+        assert int(words[9]) > 0, line               # node_cbegin walked the internal levels
