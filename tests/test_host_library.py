@@ -136,6 +136,30 @@ def test_erase_gives_the_reference_tree(rtb, kind):
     assert _same_flat(mine.flatten(), ref.flatten())
 
 
+@needs_ref
+@pytest.mark.parametrize("kind", [2, 3, 4, 5, 6, 8])
+def test_degenerate_key_sets_give_the_reference_tree(rtb, kind):
+    """ties everywhere -- all keys equal, a 3-valued lattice, collinear keys: zero-area bounds, equal
+    enlargements, equal sort keys in the split -- and the tree is still the reference's bit for bit, before and
+    after erasing a third of it"""
+    scalar, dim, is_box, _ = O.KINDS[kind]
+    dt = O.SCALAR_DTYPES[scalar]
+    rng = np.random.default_rng(900 + kind)
+    n = 1200
+    line = np.concatenate([np.linspace(0, 1, n)[:, None], np.zeros((n, dim - 1))], axis=1)
+    for name, pts, extent in (("all equal", np.repeat(rng.random((1, dim)), n, axis=0), 0.0),
+                              ("lattice", rng.integers(0, 3, (n, dim)) / 2.0, 0.25),
+                              ("collinear", line, 0.0)):
+        pts = pts.astype(dt)
+        keys = np.stack([pts, pts + dt(extent)], axis=1) if is_box else pts
+        mine, ref = rtb.RTree(kind).insert(keys), O.RefTree(kind).insert(keys)
+        assert mine.check_invariants() == 0, name
+        assert _same_flat(mine.flatten(), ref.flatten()), name
+        gone = rng.permutation(n).astype(np.uint32)[:400]
+        assert mine.erase_ids(gone) == ref.erase_ids(gone) == 400
+        assert _same_flat(mine.flatten(), ref.flatten()), name
+
+
 @pytest.mark.parametrize("kind", [0, 2, 4, 5, 6])
 def test_flatten_device_layout(rtb, kind):
     """level-ordered SoA blocks: every node's entries are those of flatten(), in slot order,
