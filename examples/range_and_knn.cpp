@@ -2,7 +2,7 @@
 // a range) moved onto the B200 engine, in the reference's own language.  Host side: this repository's
 // header-only eh::rtree (same API as the reference); device side: the C ABI of include/rtree_b200.h.
 //
-//   g++ -std=c++17 -O2 -I r-star-tree_b200/include -I include examples/range_and_knn.cpp \
+//   g++ -std=c++17 -O2 -I r-star-tree_b200/include -I include examples/range_and_knn.cpp
 //       -L r-star-tree_b200/csrc -lrtree_b200 -Wl,-rpath,$PWD/r-star-tree_b200/csrc -o range_and_knn
 //
 // It checks every GPU answer against RTree::search() on the host tree and exits non-zero on any

@@ -118,3 +118,24 @@ def test_batch_planner_never_divides_by_zero_and_covers_the_call(rtb):
     assert plan(16_000_000, 1) == plan(16_000_000, 4096)          # clamped, not divided by
     with pytest.raises(rtb.RtError):
         plan(1 << 32, mi)
+
+
+def test_cpp_example_links_and_fails_loudly_without_a_device(rtb, tmp_path):
+    """examples/range_and_knn.cpp (host header + C ABI from C++) compiles and links
+    against the in-tree library on a CPU box; run without a GPU it must stop at rt_upload with the library's error
+    text, not fall back to anything (tests/test_gpu_cpp_example.py runs it for real)"""
+    import os
+    import subprocess
+    if not _no_gpu(rtb):
+        pytest.skip("a CUDA device is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "r-star-tree_b200", "csrc")
+    exe = str(tmp_path / "range_and_knn")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror",
+                    "-I", os.path.join(root, "r-star-tree_b200", "include"), "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "range_and_knn.cpp"), "-L", csrc, "-lrtree_b200",
+                    "-Wl,-rpath," + csrc, "-o", exe], check=True)
+    out = subprocess.run([exe, "2000", "100"], capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0
+    assert "rt_upload" in out.stdout + out.stderr
+    assert "mismatching" not in out.stdout          # it never got as far as answering anything
