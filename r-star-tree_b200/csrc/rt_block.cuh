@@ -31,6 +31,30 @@
 #define RTB_ABS_SP_WIDE 1
 #endif
 
+// RTB_DEBUG_CHECKS = 1 (`make checked` -> librtree_b200_checked.so, never loaded unless RTB_LIB names it): the
+// traversal kernels assert what their design argues -- a stack never outgrows 32 entries per level, a popped link
+// names a block of the image, stash / list cursors stay inside their buffers -- and trap with a message
+// otherwise.  compute-sanitizer is closed on this pool; the GPU suite run against this build stands in for it
+// (profiles/r2_v6_pytest_gpu_checked_build.log).  0 in the product: the macro expands to nothing.
+#ifndef RTB_DEBUG_CHECKS
+#define RTB_DEBUG_CHECKS 0
+#endif
+#if RTB_DEBUG_CHECKS
+#include <cstdio>
+#define RTB_CHECK(cond, what)                                                                       \
+  do                                                                                                \
+  {                                                                                                 \
+    if (!(cond))                                                                                    \
+    {                                                                                               \
+      printf("[rtb check] %s:%d block %d thread %d: %s\n", __FILE__, __LINE__, (int)blockIdx.x,    \
+             (int)threadIdx.x, what);                                                               \
+      __trap();                                                                                     \
+    }                                                                                               \
+  } while (0)
+#else
+#define RTB_CHECK(cond, what) ((void)0)
+#endif
+
 namespace rtb
 {
 

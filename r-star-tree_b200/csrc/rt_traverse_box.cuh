@@ -238,6 +238,7 @@ box_traverse_kernel(const BoxLaunch p)
         else
           spw -= min(spw, (uint32_t)(G * 4));
         RTB_LOOP_SYNC();
+        RTB_CHECK(node <= null_link, "box traversal: popped a link beyond the image");
 
         const bool is_leaf = node >= leaf_link_begin;
         uint32_t link;
@@ -377,6 +378,8 @@ box_traverse_kernel(const BoxLaunch p)
           spw += __popc(m_int) * 4u;
         }
 
+        RTB_CHECK(spw - sp_base <= stack_cap * 4u, "box traversal: the stack outgrew 32 entries per level");
+
         // leaf entries that satisfy the predicate
         if (m_leaf != 0)
         {
@@ -393,7 +396,10 @@ box_traverse_kernel(const BoxLaunch p)
                   if (at < HIT_BUF)
                     sts_u32(warp_mem + at * 4u, link);
                   else if (PASS == PASS_STASH && at < slab_left)
-                    p.stash[slab_pos + at] = link; // beyond the hit buffer: straight into the warp's slab,
+                  {
+                    RTB_CHECK(slab_pos + at < p.stash_capacity, "box traversal: spill beyond the stash pool");
+                    p.stash[slab_pos + at] = link;
+                  } // beyond the hit buffer: straight into the warp's slab,
                                                    // at its final place there (sorted after the gather)
                 }
                 else if (PASS == PASS_WRITE && at < expect)
@@ -498,6 +504,7 @@ box_traverse_kernel(const BoxLaunch p)
         {
           if (slab_left >= count)
           {
+            RTB_CHECK(slab_pos + count <= p.stash_capacity, "box traversal: short list beyond the stash pool");
             uint32_t v = ((uint32_t)lane < count) ? lds_u32(warp_mem + lane * 4u) : RT_INVALID_ID;
             if (p.sorted)
               v = warp_sort32(v, lane, count);
@@ -512,6 +519,7 @@ box_traverse_kernel(const BoxLaunch p)
         {
           // a list that outgrew the hit buffer but not the slab: ids HIT_BUF.. are in the slab
           // already (every one of them had at < slab_left), the first HIT_BUF join them
+          RTB_CHECK(slab_pos + count <= p.stash_capacity, "box traversal: long list beyond the stash pool");
           p.stash[slab_pos + lane] = lds_u32(warp_mem + lane * 4u);
           where = (uint32_t)slab_pos;
           slab_pos += count;
@@ -528,6 +536,7 @@ box_traverse_kernel(const BoxLaunch p)
           p.stash_pos[qi] = where;
           if (where == NO_STASH)
           {
+            RTB_CHECK(*p.deferred_count < p.n, "box traversal: more deferred queries than queries");
             p.deferred_list[atomicAdd(p.deferred_count, 1u)] = defer_key;
             atomicMax(p.max_list, count); // the second traversal writes it, the segment sort orders it
           }

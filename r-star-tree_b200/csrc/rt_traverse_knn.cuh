@@ -110,6 +110,7 @@ knn_traverse_kernel(const KnnLaunch p)
         lds_u32x2(stack_pop + sp8, node, node_d2);
         sp8 -= min(sp8, (uint32_t)(G * 8));
         RTB_LOOP_SYNC();
+        RTB_CHECK(node <= null_link, "kNN traversal: popped a link beyond the image");
         if (node_d2 > wd) // the bound has moved past this node since it was pushed
           node = null_link;
 
@@ -153,6 +154,7 @@ knn_traverse_kernel(const KnnLaunch p)
           if (push)
             sts_u32x2(stack + sp8 + at * 8u, link, d2b);
           sp8 += __popc(m_push) * 8u;
+          RTB_CHECK(sp8 <= stack_cap * 8u, "kNN traversal: the stack outgrew 32 entries per level");
         }
 
         // ---- leaf entries that beat the worst of the k best: inserted one at a time, nearest first ----

@@ -127,6 +127,7 @@ ray_traverse_kernel(const RayLaunch p)
         const uint32_t node = lds_u32(stack_pop + sp4);
         sp4 -= min(sp4, (uint32_t)(G * 4));
         RTB_LOOP_SYNC();
+        RTB_CHECK(node <= null_link, "ray traversal: popped a link beyond the image");
 
         const bool is_leaf = node >= leaf_link_begin;
         uint32_t link;
@@ -162,6 +163,7 @@ ray_traverse_kernel(const RayLaunch p)
         if (hit && !is_leaf)
           sts_u32(stack + sp4 + __popc(m_int & lt_mask) * 4u, link);
         sp4 += __popc(m_int) * 4u;
+        RTB_CHECK(sp4 <= stack_cap * 4u, "ray traversal: the stack outgrew 32 entries per level");
 
         if (m_leaf != 0)
         {
