@@ -683,6 +683,13 @@ def section_config5(cx, c5):
             "query_generation_s": round(t_gen, 1),
             "parity": parity,
         }
+        if cx.cpu_arm and c5.get("ref") is not None:
+            n_cpu = int(min(calls[0][2], env_int("RTB_REF_C5", 1_000_000)))
+            threads = host_threads()
+            s, _ = c5["ref"].time_search_boxes(calls[0][0].numpy()[:n_cpu], threads=threads)
+            section["cpu_baseline"] = {"value": n_cpu / s, "unit": UNIT, "cores": threads, "kind": "reference",
+                                       "sample": "reference RTree::search() on the first %d queries of the batch, OpenMP "
+                                                 "over %d threads (%.1f s)" % (n_cpu, threads, s)}
     tree.close()
     return section
 
